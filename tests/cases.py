@@ -1,0 +1,138 @@
+"""Case definitions shared by the oracle tests and the GPU parity tests.
+
+Each case transcribes the constants of one reference example's ``params.py`` /
+driver (cited), builds the coefficient fields with the oracle's field builders
+(O(n) host formulas from helmholtz_x/parameters_utils.py) and returns plain numpy
+inputs; nothing here reads /root/reference.
+"""
+import json
+import os
+
+import numpy as np
+
+from oracle import hx_oracle as ox
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_values():
+    with open(os.path.join(GOLDEN_DIR, "golden_values.json")) as fh:
+        return json.load(fh)
+
+
+def cplx(pair):
+    return complex(pair[0], pair[1])
+
+
+_mesh_cache = {}
+
+
+def mesh(name):
+    if name not in _mesh_cache:
+        _mesh_cache[name] = ox.load_mesh_npz(os.path.join(GOLDEN_DIR, name + "_mesh.npz"))
+    return _mesh_cache[name]
+
+
+class Case(dict):
+    __getattr__ = dict.__getitem__
+
+
+def rijke3d():
+    """numerical_examples/Longitudinal/NetworkCode/RijkeTube3D/{params,active}.py (config 1)."""
+    m = mesh("rijke3d")
+    gamma = 1.4; p_amb = 1e5; rho_u = 1.22; rho_d = 0.85; r_gas = 287.0
+    c_u = np.sqrt(gamma * p_amb / rho_u); c_d = np.sqrt(gamma * p_amb / rho_d)
+    T_u = c_u ** 2 / (gamma * r_gas); T_d = c_d ** 2 / (gamma * r_gas)
+    x_f = np.array([[0.0, 0.0, 0.25]]); x_r = np.array([[0.0, 0.0, 0.20]])
+    return Case(
+        mesh=m, degree=1, bcs={1: {"Neumann"}, 2: {"Neumann"}, 3: {"Neumann"}},
+        c=ox.step_field(m, x_f, c_u, c_d), c_passive=ox.step_field(m, x_f, c_u, c_u),
+        parameter_is_temperature=False, c_is_dg0=False,
+        flame="distributed", w=ox.gaussian_function(m, x_r, 0.025), h=ox.gaussian_function(m, x_f, 0.025),
+        rho=ox.rho_step(m, x_f, 0.025, rho_d, rho_u), T=ox.step_field(m, x_f, T_u, T_d), gamma=None,
+        q_0=-27.008910380099735, u_b=0.10066660027273297, ftf=("ntau", 0.1, 0.0015),
+        target=200 * 2 * np.pi, nev=2, tol=1e-8)
+
+
+def prf_rijke3d():
+    """numerical_examples/Longitudinal/PRF/RijkeTube3D/{params,active}.py (Robin, nondimensional, PEP)."""
+    m = mesh("rijke3d")
+    r_gas = 287.0; gamma = 1.4; p_amb = 1e5; c_amb = 339.0
+    rho_in = 1.22; rho_out = 0.85
+    c_in = np.sqrt(gamma * p_amb / rho_in); c_out = np.sqrt(gamma * p_amb / rho_out)
+    T_in = p_amb / (r_gas * rho_in); T_out = p_amb / (r_gas * rho_out)
+    U = c_amb; Lr = 1.0
+    rho_u = rho_in * U ** 2 / p_amb; rho_d = rho_out * U ** 2 / p_amb
+    x_f = np.array([[0.0, 0.0, 0.25]]); x_r = np.array([[0.0, 0.0, 0.20]])
+    R = -0.975 - 0.05j
+    return Case(
+        mesh=m, degree=1, bcs={1: {"Neumann"}, 2: {"Robin": R}, 3: {"Robin": R}},
+        c=ox.step_field(m, x_f, c_in / U, c_out / U), parameter_is_temperature=False, c_is_dg0=False,
+        flame="distributed", w=ox.gaussian_function(m, x_r, 0.025), h=ox.gaussian_function(m, x_f, 0.025),
+        rho=ox.rho_step(m, x_f, 0.025, rho_d, rho_u),
+        T=ox.step_field(m, x_f, T_in * r_gas / U ** 2, T_out * r_gas / U ** 2), gamma=1.4,
+        q_0=200.0, u_b=0.1, ftf=("ntau", 0.014 / (p_amb * Lr ** 2), 0.0015 * U / Lr),
+        target=np.pi, nev=2, tol=1e-8)
+
+
+def rijkeffd():
+    """numerical_examples/ShapeSensitivities/RijkeFFD/{params,main}.py (config 5 eigenpair)."""
+    m = mesh("rijkeffd")
+    r_gas = 287.0; p_amb = 1e5; rho_u = 1.22; rho_d = 0.85
+    T_in = p_amb / (r_gas * rho_u); T_out = p_amb / (r_gas * rho_d)
+    x_f = np.array([[0.0, 0.0, 0.25]]); x_r = np.array([[0.0, 0.0, 0.20]])
+    R = -0.975 - 0.05j
+    T = ox.step_field(m, x_f, T_in, T_out)
+    return Case(
+        mesh=m, degree=1, bcs={1: {"Neumann"}, 2: {"Robin": R}, 3: {"Robin": R}},
+        c=T, parameter_is_temperature=True, c_is_dg0=False,
+        flame="distributed", w=ox.gaussian_function(m, x_r, 0.025), h=ox.gaussian_function(m, x_f, 0.025),
+        rho=ox.rho_step(m, x_f, 0.025, rho_d, rho_u), T=T, gamma=1.4,
+        q_0=200.0, u_b=0.1, ftf=("ntau", 0.014, 0.0015),
+        target=180 * 2 * np.pi, nev=2, tol=1e-8)
+
+
+def annulus_c(m):
+    """fullAnnulus/params.py:53-70: DG0 speed of sound from the cell midpoint z."""
+    z = m.x[m.cells].mean(axis=1)[:, 2]
+    gamma = 1.4; r = 287.0; l_cc = 0.2; T_amb = 300.0; T_a = 1521.0; T_b = 1200.0
+    c = np.full(m.n_cells, np.sqrt(gamma * r * T_b))
+    c[z < 0] = np.sqrt(gamma * r * T_amb)
+    mid = (z > 0) & (z < l_cc)
+    c[mid] = np.sqrt(gamma * r * ((T_b - T_a) * (z[mid] / l_cc) ** 2 + T_a))
+    return c
+
+
+def annulus(degree=1):
+    """numerical_examples/AnnularCombustor/Micca/fullAnnulus/{params,active_fpi,active_newton}.py (config 3)."""
+    m = mesh("annulus")
+    r_f = 0.14 + 0.035; theta = np.deg2rad(22.5); z_r = -0.02; N = 16
+    x_r = np.array([[r_f * np.cos(i * theta), r_f * np.sin(i * theta), z_r] for i in range(N)])
+    rho_amb = 101325.0 / (287.0 * 300.0)
+    ftf = np.load(os.path.join(GOLDEN_DIR, "annulus_ftf.npz"))
+    return Case(
+        mesh=m, degree=degree, bcs={11: {"Robin": -0.875 - 0.2j}},
+        c=annulus_c(m), parameter_is_temperature=False, c_is_dg0=True,
+        flame="pointwise", x_r=x_r, h=ox.q_multiple(m, N), rho_u=rho_amb, gamma=1.4,
+        q_0=2080.0, u_b=0.66, ftf=("statespace", ftf["A"], ftf["b"], ftf["c"], ftf["d"]),
+        target=3225.120 + 481.0j, nev=4, tol=1e-3, newton_init=3260 + 460j, newton_nev=2, newton_tol=1e-2)
+
+
+def make_ftf(spec):
+    if spec[0] == "ntau":
+        return ox.NTau(spec[1], spec[2])
+    return ox.StateSpace(*spec[1:])
+
+
+def oracle_operators(case, passive=False):
+    c = case["c_passive"] if passive else case["c"]
+    return ox.acoustic_matrices(case.mesh, case.bcs, c, case.degree, case.parameter_is_temperature, case.c_is_dg0)
+
+
+def oracle_flame(case):
+    ftf = make_ftf(case.ftf)
+    if case.flame == "distributed":
+        return ox.distributed_flame(case.mesh, case.w, case.h, case.rho, case.T, case.q_0, case.u_b, ftf,
+                                    case.degree, gamma=case.gamma)
+    return ox.pointwise_flame(case.mesh, case.x_r, case.h, case.rho_u, case.q_0, case.u_b, ftf, case.degree,
+                              gamma=case.gamma)
