@@ -1,0 +1,237 @@
+"""Smoothed-aggregation multigrid preconditioner for the shifted operator
+P(sigma) = A + sigma B + sigma^2 C  -- the iterative stand-in for the exact LU
+(PETSc LU / MUMPS) behind SLEPc's ST 'sinvert' (helmholtz_x/eigensolvers.py:49-50,
+102-103).
+
+Set-up (once per mesh; sigma-independent):
+  * aggregates = runs of `agg_size` dofs along a Morton (Z-order) curve through the
+    dof coordinates (embarrassingly parallel: one sort);
+  * tentative prolongator T (piecewise constant, normalised), smoothed with one damped
+    Jacobi step on the SPD surrogate K = -A + tau C:  P = (I - 4/(3 rho) D^-1 K) T;
+  * Galerkin coarse operators A_c = P^T A P, B_c, C_c on a common coarse pattern.
+  The sparse products of the set-up go through torch.sparse (cuSPARSE SpGEMM): library
+  plumbing outside the per-iteration path.
+Per shift (every outer fixed-point / Newton step): one `combine_abc` kernel per level
+forms P_l(sigma) on that level's pattern, one Gauss-Jordan kernel inverts the coarsest.
+Per application: V(nu,nu) cycle of damped-Jacobi sweeps, CSR SpMVs for restriction /
+prolongation and a dense GEMV on the coarsest level -- all libhx_b200 kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .backend import CsrMatrix
+
+c128 = torch.complex128
+f64 = torch.float64
+
+
+# ---- torch sparse helpers (set-up only) -------------------------------------------------
+def _rows_of(indptr, nnz):
+    n = indptr.numel() - 1
+    return torch.repeat_interleave(torch.arange(n, device=indptr.device), (indptr[1:] - indptr[:-1]).long(),
+                                   output_size=nnz)
+
+
+def _to_coo(M: CsrMatrix, values=None):
+    vals = M.values if values is None else values
+    rows = _rows_of(M.indptr, M.nnz)
+    return torch.sparse_coo_tensor(torch.stack([rows, M.indices.long()]), vals, size=M.shape).coalesce()
+
+
+def _from_coo(T) -> CsrMatrix:
+    T = T.coalesce()
+    idx = T.indices()
+    n_rows, n_cols = T.shape
+    counts = torch.bincount(idx[0], minlength=n_rows)
+    indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=idx.device)
+    indptr[1:] = torch.cumsum(counts, 0)
+    return CsrMatrix(n_rows, n_cols, indptr.to(torch.int32).contiguous(), idx[1].to(torch.int32).contiguous(),
+                     T.values().contiguous())
+
+
+def _spmm(A, B):
+    return torch.sparse.mm(A, B).coalesce()
+
+
+def _diag(M: CsrMatrix):
+    rows = _rows_of(M.indptr, M.nnz)
+    mask = M.indices.long() == rows
+    d = torch.zeros(M.n_rows, dtype=M.values.dtype, device=M.values.device)
+    d[rows[mask]] = M.values[mask]
+    return d
+
+
+def morton_order(coords, bits=16):
+    """Permutation sorting points along a 3-D Z-order curve."""
+    lo = coords.min(dim=0).values
+    ext = (coords.max(dim=0).values - lo).max().clamp_min(1e-300)
+    q = ((coords - lo) / ext * (2 ** bits - 1)).long().clamp_(0, 2 ** bits - 1)
+    key = torch.zeros(coords.shape[0], dtype=torch.int64, device=coords.device)
+    for b in range(bits):
+        for d in range(3):
+            key |= ((q[:, d] >> b) & 1) << (3 * b + d)
+    return torch.sort(key, stable=True).indices
+
+
+def _values_on(pattern_keys, T, n_cols):
+    """Values of coalesced COO tensor T laid out on the sorted key list pattern_keys."""
+    idx = T.indices()
+    keys = idx[0] * n_cols + idx[1]
+    pos = torch.searchsorted(pattern_keys, keys)
+    out = torch.zeros(pattern_keys.numel(), dtype=T.values().dtype, device=keys.device)
+    out[pos] = T.values()
+    return out
+
+
+class Level:
+    pass
+
+
+class AMG:
+    def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=8,
+                 coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0):
+        """A, C real-valued, B complex or None -- all on ONE shared fine pattern."""
+        self.be, self.nu, self.omega = be, nu, omega
+        dev = A.values.device
+        self.levels = []
+        a_re = A.values
+        c_re = C.values
+        b_cx = B.values if B is not None else None
+        if tau is None:
+            # shift making K = -A + tau C safely SPD and of the size of the operator's low spectrum
+            dA = _diag(A).abs().max()
+            dC = _diag(C).abs().max()
+            tau = float(1e-3 * dA / dC)
+        pat = A
+        coords = coords.to(dev)
+        while True:
+            L = Level()
+            L.n = pat.n_rows
+            L.pattern = pat
+            L.a, L.c, L.b = a_re, c_re, b_cx
+            self.levels.append(L)
+            if L.n <= coarse_max or len(self.levels) >= max_levels:
+                break
+            n = L.n
+            order = morton_order(coords)
+            agg = torch.empty(n, dtype=torch.int64, device=dev)
+            agg[order] = torch.arange(n, device=dev) // agg_size
+            nc = int(agg.max().item()) + 1
+            cnt = torch.bincount(agg, minlength=nc).to(f64)
+            tval = 1.0 / torch.sqrt(cnt[agg])
+            T = torch.sparse_coo_tensor(torch.stack([torch.arange(n, device=dev), agg]), tval, size=(n, nc)).coalesce()
+            kval = -a_re + tau * c_re
+            K = _to_coo(pat, kval)
+            d = _diag(pat.with_values(kval))
+            rows = K.indices()[0]
+            S = torch.sparse_coo_tensor(K.indices(), K.values() / d[rows], size=K.shape).coalesce()
+            # spectral radius of D^-1 K by a few power iterations
+            v = torch.ones(n, 1, dtype=f64, device=dev) + 0.1 * torch.sin(torch.arange(n, device=dev, dtype=f64)).view(-1, 1)
+            rho = 1.0
+            for _ in range(12):
+                v = torch.sparse.mm(S, v)
+                rho = float(torch.linalg.norm(v))
+                v = v / rho
+            ST = _spmm(S, T)
+            Pm = (T - (4.0 / (3.0 * rho)) * ST).coalesce()
+            Rm = Pm.t().coalesce()
+            Ac = _spmm(Rm, _spmm(_to_coo(pat, a_re), Pm))
+            Cc = _spmm(Rm, _spmm(_to_coo(pat, c_re), Pm))
+            mats = [Ac, Cc]
+            if b_cx is not None:
+                Br = _spmm(Rm, _spmm(_to_coo(pat, b_cx.real.contiguous()), Pm))
+                Bi = _spmm(Rm, _spmm(_to_coo(pat, b_cx.imag.contiguous()), Pm))
+                mats += [Br, Bi]
+            keys = torch.unique(torch.cat([m.indices()[0] * nc + m.indices()[1] for m in mats]))
+            crow, ccol = keys // nc, keys % nc
+            counts = torch.bincount(crow, minlength=nc)
+            indptr = torch.zeros(nc + 1, dtype=torch.int64, device=dev)
+            indptr[1:] = torch.cumsum(counts, 0)
+            L.P = _from_coo(Pm)
+            L.R = _from_coo(Rm)
+            pat = CsrMatrix(nc, nc, indptr.to(torch.int32).contiguous(), ccol.to(torch.int32).contiguous(),
+                            torch.zeros(keys.numel(), dtype=f64, device=dev))
+            a_re = _values_on(keys, Ac, nc)
+            c_re = _values_on(keys, Cc, nc)
+            if b_cx is not None:
+                b_cx = torch.complex(_values_on(keys, Br, nc), _values_on(keys, Bi, nc))
+            csum = torch.zeros(nc, 3, dtype=f64, device=dev)
+            csum.index_add_(0, agg, coords)
+            coords = csum / cnt.view(-1, 1)
+        # work vectors
+        for L in self.levels:
+            L.x = be.zeros(L.n); L.b_ = be.zeros(L.n); L.r = be.zeros(L.n); L.t = be.zeros(L.n)
+            L.M = None
+            L.dinv = be.zeros(L.n)
+        self.coarse_inv = None
+
+    @property
+    def sizes(self):
+        return [L.n for L in self.levels]
+
+    @property
+    def operator_complexity(self):
+        return sum(L.pattern.nnz for L in self.levels) / self.levels[0].pattern.nnz
+
+    def set_shift(self, ca, cb, cc, fine_values=None):
+        """Form P_l = ca*A_l + cb*B_l + cc*C_l on every level; invert the coarsest."""
+        be = self.be
+        for i, L in enumerate(self.levels):
+            if i == 0 and fine_values is not None:
+                vals = fine_values
+            else:
+                vals = be.empty(L.pattern.nnz)
+                be.combine_abc(L.a, L.b, L.c, ca, cb, cc, vals)
+            L.M = L.pattern.with_values(vals)
+            if i < len(self.levels) - 1:
+                be.diag_inv(L.M, L.dinv)
+        L = self.levels[-1]
+        dense = torch.zeros(L.n, L.n, dtype=c128, device=L.M.values.device)
+        rows = _rows_of(L.M.indptr, L.M.nnz)
+        # column-major storage of the coarse matrix == row-major storage of its transpose
+        dense[L.M.indices.long(), rows] = L.M.values
+        info = be.dense_inverse(dense)
+        self.coarse_inv = dense
+        self._coarse_info = info
+        return self
+
+    def fine_matrix(self):
+        return self.levels[0].M
+
+    def _smooth(self, L, b, x, first_zero):
+        """nu damped-Jacobi sweeps; result ends in L.x.  x is L.x."""
+        be = self.be
+        cur, other = L.x, L.t
+        n_sweeps = self.nu
+        if first_zero:
+            be.jacobi_sweep(L.M, L.dinv, b, None, cur, self.omega)
+            n_sweeps -= 1
+        for _ in range(n_sweeps):
+            be.jacobi_sweep(L.M, L.dinv, b, cur, other, self.omega)
+            cur, other = other, cur
+        if cur is not L.x:
+            L.x, L.t = cur, other      # swap the roles of the buffers
+
+    def _cycle(self, i, b):
+        """Solve approximately M_i x = b; result in self.levels[i].x."""
+        be = self.be
+        L = self.levels[i]
+        if i == len(self.levels) - 1:
+            be.dense_gemv(self.coarse_inv, b, L.x)
+            return L.x
+        self._smooth(L, b, L.x, first_zero=True)
+        be.spmv(L.M, L.x, L.r, alpha=-1.0, beta=1.0, y0=b)           # r = b - M x
+        Lc = self.levels[i + 1]
+        be.spmv(L.R, L.r, Lc.b_)
+        xc = self._cycle(i + 1, Lc.b_)
+        be.spmv(L.P, xc, L.x, alpha=1.0, beta=1.0, y0=L.x)             # x += P xc
+        self._smooth(L, b, L.x, first_zero=False)
+        return L.x
+
+    def apply(self, v, out):
+        """out = V-cycle(v)."""
+        x = self._cycle(0, v)
+        out.copy_(x)
+        return out

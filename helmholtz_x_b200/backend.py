@@ -1,0 +1,213 @@
+"""Device backend: torch owns memory/streams, every numerical kernel is a call into
+libhx_b200.so.  Host-side algorithms (krylov.py, amg.py, eigensolvers.py) are written
+against this small interface; ``tests`` substitute a NumPy/torch-CPU test double
+(``oracle/host_backend.py``) to exercise that host logic without a GPU.  The product
+never constructs anything but :class:`CudaBackend`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+c128 = torch.complex128
+f64 = torch.float64
+
+
+def _c2(z):
+    z = complex(z)
+    return (C.c_double * 2)(z.real, z.imag)
+
+
+def choose_lanes(nnz, n_rows):
+    mean = nnz / max(n_rows, 1)
+    if mean <= 6:
+        return 4
+    if mean <= 20:
+        return 8
+    if mean <= 48:
+        return 16
+    return 32
+
+
+@dataclass
+class CsrMatrix:
+    """CSR matrix on the device: int32 indptr/indices, float64 or complex128 values."""
+    n_rows: int
+    n_cols: int
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    values: torch.Tensor
+
+    @property
+    def nnz(self):
+        return int(self.indices.numel())
+
+    @property
+    def shape(self):
+        return (self.n_rows, self.n_cols)
+
+    @property
+    def lanes(self):
+        return choose_lanes(self.nnz, self.n_rows)
+
+    def with_values(self, values):
+        return CsrMatrix(self.n_rows, self.n_cols, self.indptr, self.indices, values)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.values.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                             shape=self.shape)
+
+
+@dataclass
+class LowRank:
+    """sum_f left_f right_f^T kept as sparse vectors (flame operator, never densified).
+
+    right: CSR-like over flames (rptr, ridx, rval); left: rows of the union support
+    (lrow) each with (flame, value) pairs (lptr, lcol, lval)."""
+    n: int
+    r: int
+    rptr: torch.Tensor
+    ridx: torch.Tensor
+    rval: torch.Tensor
+    lrow: torch.Tensor
+    lptr: torch.Tensor
+    lcol: torch.Tensor
+    lval: torch.Tensor
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.HxLibraryError("helmholtz_x_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._scratch = {}
+
+    # ---- plumbing -------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def zeros(self, *shape, dtype=c128):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def empty(self, *shape, dtype=c128):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def asarray(self, a, dtype=None):
+        return torch.as_tensor(a, dtype=dtype, device=self.device).contiguous()
+
+    def scratch(self, k):
+        key = max(8, 1 << (max(k, 1) - 1).bit_length())
+        if key not in self._scratch:
+            nbytes = _lib.call("hx_reduce_scratch_bytes", key)
+            self._scratch[key] = torch.zeros(nbytes // 8 + 1, dtype=f64, device=self.device)
+        return self._scratch[key]
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    # ---- sparse -----------------------------------------------------------------
+    def spmv(self, M: CsrMatrix, x, y, alpha=1.0, beta=None, y0=None, lanes=None):
+        """y = alpha*M@x (+ beta*y0)."""
+        assert x.dtype == c128 and y.dtype == c128 and x.is_contiguous() and y.is_contiguous()
+        assert x.numel() >= M.n_cols and y.numel() >= M.n_rows
+        name = "hx_spmv_zz" if M.values.dtype == c128 else "hx_spmv_dz"
+        y0p = None
+        if beta is not None:
+            y0p = (y0 if y0 is not None else y).data_ptr()
+        _lib.call(name, M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(), x.data_ptr(),
+                  y.data_ptr(), _c2(alpha), _c2(beta if beta is not None else 0.0), y0p, lanes or M.lanes, self.stream)
+        return y
+
+    def combine_abc(self, a, b, c, ca, cb, cc, out):
+        nnz = out.numel()
+        _lib.call("hx_combine_abc", nnz, a.data_ptr() if a is not None else None,
+                  b.data_ptr() if b is not None else None, c.data_ptr() if c is not None else None,
+                  _c2(ca), _c2(cb), _c2(cc), out.data_ptr(), self.stream)
+        return out
+
+    def lowrank_dots(self, lr: LowRank, x, t, transpose=False):
+        """t_f = right_f^T x  (transpose=True uses the left vectors: adjoint problem)."""
+        if transpose:
+            raise NotImplementedError
+        _lib.call("hx_lowrank_dots", lr.r, lr.rptr.data_ptr(), lr.ridx.data_ptr(), lr.rval.data_ptr(), x.data_ptr(),
+                  t.data_ptr(), self.stream)
+        return t
+
+    def lowrank_update(self, lr: LowRank, t, coef, y):
+        """y += coef * sum_f left_f t_f."""
+        _lib.call("hx_lowrank_update", int(lr.lrow.numel()), lr.lrow.data_ptr(), lr.lptr.data_ptr(), lr.lcol.data_ptr(),
+                  lr.lval.data_ptr(), t.data_ptr(), _c2(coef), y.data_ptr(), self.stream)
+        return y
+
+    # ---- Krylov basis ---------------------------------------------------------------
+    def multi_dot(self, V, k, w, out, conj=True):
+        """out[j] = <V[j], w>, j<k; V is (m, n) row-major."""
+        n = w.numel()
+        _lib.call("hx_multi_dot", n, k, V.data_ptr(), V.stride(0), w.data_ptr(), 1 if conj else 0, out.data_ptr(),
+                  self.scratch(k).data_ptr(), self.stream)
+        return out
+
+    def multi_axpy(self, V, k, h, w, hacc=None, nrm2=None):
+        """w -= sum_j h[j] V[j]; hacc += h; nrm2 (device float64 view) = ||w||^2."""
+        n = w.numel()
+        _lib.call("hx_multi_axpy", n, k, V.data_ptr(), V.stride(0), h.data_ptr(), w.data_ptr(),
+                  hacc.data_ptr() if hacc is not None else None, nrm2.data_ptr() if nrm2 is not None else None,
+                  self.scratch(1).data_ptr(), self.stream)
+        return w
+
+    def scale_copy(self, w, out, nrm2=None, alpha=None):
+        """out = w/sqrt(nrm2[0]) (device scalar) or alpha*w."""
+        _lib.call("hx_scale_copy", w.numel(), w.data_ptr(), nrm2.data_ptr() if nrm2 is not None else None,
+                  _c2(alpha if alpha is not None else 1.0), out.data_ptr(), self.stream)
+        return out
+
+    def axpby(self, a, x, b, y):
+        """y = a*x + b*y."""
+        _lib.call("hx_axpby", y.numel(), _c2(a), x.data_ptr(), _c2(b) if b is not None else None, y.data_ptr(), self.stream)
+        return y
+
+    def basis_rotate(self, V, m, Q, kout, Vout):
+        """Vout[c] = sum_j Q[c, j] V[j]  (Q: (kout, m) row-major tensor = column-major m x kout)."""
+        assert Q.is_contiguous() and Q.shape[1] >= m
+        n = V.shape[1]
+        _lib.call("hx_basis_rotate", n, m, kout, V.data_ptr(), V.stride(0), Q.data_ptr(), Q.stride(0), Vout.data_ptr(),
+                  Vout.stride(0), self.stream)
+        return Vout
+
+    # ---- preconditioner pieces -----------------------------------------------------------
+    def diag_inv(self, M: CsrMatrix, out):
+        _lib.call("hx_extract_diag_inv", M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(),
+                  out.data_ptr(), self.stream)
+        return out
+
+    def jacobi_sweep(self, M: CsrMatrix, dinv, b, xin, xout, omega):
+        _lib.call("hx_jacobi_sweep", M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(),
+                  dinv.data_ptr(), b.data_ptr(), xin.data_ptr() if xin is not None else None, xout.data_ptr(),
+                  float(omega), M.lanes, self.stream)
+        return xout
+
+    def dense_inverse(self, A):
+        """In-place inverse of a column-major n x n complex matrix; returns info tensor (0 = ok)."""
+        n = A.shape[0]
+        info = torch.zeros(n + 1, dtype=torch.int32, device=self.device)
+        _lib.call("hx_dense_inverse", n, A.data_ptr(), info.data_ptr(), self.stream)
+        return info
+
+    def dense_gemv(self, A, x, y):
+        _lib.call("hx_dense_gemv", A.shape[0], A.data_ptr(), x.data_ptr(), y.data_ptr(), self.stream)
+        return y
+
+    def launch_count(self):
+        return int(_lib.call("hx_launch_count"))
+
+    def reset_launch_count(self):
+        _lib.load().hx_launch_count_reset()

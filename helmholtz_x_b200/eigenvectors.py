@@ -1,0 +1,85 @@
+"""helmholtz_x/eigenvectors.py: normalize_eigenvector (a11), normalize_adjoint (a13)."""
+import numpy as np
+import torch
+
+from .eigensolvers import EPS, PEP
+from .fem import Function, assemble_AC, functionspace
+from .petsc4py_utils import FixSign, matrix_vector, multiply, vector_matrix_vector
+from .solver_utils import info, rank0
+
+
+def _mass_form(V, matrices, vec):
+    """p^T M p with the UNCONJUGATED mass form p*p*dx (eigenvectors.py:47): SpMV + dot on the device."""
+    be = V.be
+    if not hasattr(V, "_mass"):
+        ones = np.ones(V.mesh.n_nodes)
+        _, cvals = assemble_AC(V, ones)
+        V._mass = V.matrix(cvals)
+    x = be.asarray(np.asarray(vec, complex), dtype=torch.complex128)
+    y = be.zeros(V.n)
+    be.spmv(V._mass, x, y)
+    out = be.zeros(2)
+    be.multi_dot(x.view(1, -1), 1, y, out, conj=False)
+    return complex(out[0].cpu().numpy())
+
+
+def normalize_eigenvector(mesh, obj, i, absolute=False, degree=1, which='right', BlochRemapper=None, matrices=None,
+                          print_eigs=True):
+    """Extract eigenvector i, FixSign, scale so that int p p dx = 1 (eigenvectors.py:11-64)."""
+    A = obj.getOperators()[0]
+    vr, vi = A.createVecs()
+    if isinstance(obj, EPS):
+        eig = obj.getEigenvalue(i)
+        omega = np.sqrt(eig)
+        if which == 'right':
+            obj.getEigenvector(i, vr, vi)
+        elif which == 'left':
+            obj.getLeftEigenvector(i, vr, vi)
+    elif isinstance(obj, PEP):
+        eig = obj.getEigenpair(i, vr, vi)
+        omega = eig
+    if BlochRemapper:
+        vr = matrix_vector(BlochRemapper, vr)
+    if matrices:
+        V = matrices.V
+    else:
+        V = functionspace(mesh, ("CG", degree))
+    p = Function(V)
+    FixSign(vr)
+    p.x.petsc_vec.setArray(vr.array)
+    meas = np.sqrt(_mass_form(V, matrices, p.x.array))
+    temp = vr.array / meas
+    if absolute:
+        abs_temp = abs(temp)
+        temp = abs_temp / np.amax(abs_temp)
+    p_normalized = Function(V)
+    p_normalized.x.petsc_vec.setArray(temp)
+    if rank0() and print_eigs:
+        print(f"Eigenvalue-> {omega:.6f} | Eigenfrequency-> {omega/(2*np.pi):.6f}\n ")
+    return omega, p_normalized
+
+
+def normalize_adjoint(omega_dir, p_dir, p_adj, matrices, D=None):
+    """p_adj <- p_adj / (p_adj . dL/domega p_dir) with the reference's dot convention
+    (eigenvectors.py:125-177)."""
+    info("- Normalizing the adjoint eigenvector to calculate shape derivatives..")
+    B = matrices.B
+    p_dir_vec = p_dir.x.petsc_vec
+    p_adj_vec = p_adj.x.petsc_vec
+    if not B and not D:
+        dL_domega = matrices.C * (2 * omega_dir)
+    elif B and not D:
+        dL_domega = (B + matrices.C * (2 * omega_dir))
+    elif D and not B:
+        dL_domega = (matrices.C * (2 * omega_dir) - D.get_derivative(omega_dir))
+    else:
+        dL_domega = (B + matrices.C * (2 * omega_dir) - D.get_derivative(omega_dir))
+    meas = vector_matrix_vector(p_adj_vec, dL_domega, p_dir_vec)
+    p_adj_vec = multiply(p_adj_vec, 1 / meas)
+    p_adj1 = p_adj
+    p_adj1.name = "p_adj"
+    p_adj1.x.petsc_vec.setArray(p_adj_vec.getArray())
+    integral = vector_matrix_vector(p_adj1.x.petsc_vec, dL_domega, p_dir_vec)
+    if rank0():
+        print("! Normalization Check: ", integral)
+    return p_adj1

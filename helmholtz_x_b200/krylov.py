@@ -1,0 +1,239 @@
+"""Host-side Krylov logic: restarted GMRES (inner solve behind the spectral
+transformation) and Krylov-Schur (what SLEPc's EPS 'krylovschur' does for
+helmholtz_x/eigensolvers.py:41-67).  All vector work happens in backend kernels
+(block classical Gram-Schmidt with re-orthogonalisation: multi_dot -> multi_axpy twice);
+the host only sees the (m+1) x m projected matrix.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+c128 = torch.complex128
+
+
+class ArnoldiBasis:
+    """(m+1) x n basis plus the device buffers of one CGS2 step."""
+
+    def __init__(self, be, n, m):
+        self.be, self.n, self.m = be, n, m
+        self.V = be.zeros(m + 1, n)
+        self.w = be.zeros(n)
+        self.h1 = be.zeros(m + 2)
+        self.h2 = be.zeros(m + 2)
+        self._h1r = torch.view_as_real(self.h1)
+
+    def orthogonalize(self, j):
+        """CGS2 of self.w against V[0..j]; stores the normalised result in V[j+1].
+        Returns (h[0..j], beta) on the host."""
+        be, V, w, k = self.be, self.V, self.w, j + 1
+        be.multi_dot(V, k, w, self.h1)
+        be.multi_axpy(V, k, self.h1, w)
+        be.multi_dot(V, k, w, self.h2)
+        nrm2 = self._h1r[k]          # real part of h1[k] receives ||w||^2
+        be.multi_axpy(V, k, self.h2, w, hacc=self.h1, nrm2=nrm2)
+        be.scale_copy(w, V[j + 1], nrm2=nrm2)
+        host = self.h1[:k + 1].cpu().numpy()
+        beta = float(np.sqrt(max(host[k].real, 0.0)))
+        return host[:k].copy(), beta
+
+
+def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, basis=None, work=None):
+    """Right-preconditioned restarted GMRES: solves A x = b, x overwritten (start 0).
+    apply_A(v, out), precond(v, out).  Returns (iterations, relative residual)."""
+    n = b.numel()
+    if basis is None:
+        basis = ArnoldiBasis(be, n, restart)
+    m = basis.m
+    V, w = basis.V, basis.w
+    z = work if work is not None else be.zeros(n)
+    x.zero_()
+    r = V[0]
+    r.copy_(b)
+    nb = be.zeros(2)
+    nbr = torch.view_as_real(nb)
+    be.multi_dot(b.view(1, -1), 1, b, nb)
+    bnorm = float(np.sqrt(nb[:1].cpu().numpy()[0].real))
+    if bnorm == 0.0:
+        return 0, 0.0
+    beta = bnorm
+    total = 0
+    rel = 1.0
+    first = True
+    while total < maxiter:
+        if not first:
+            # true residual r = b - A x
+            apply_A(x, w)
+            be.axpby(1.0, b, -1.0, w)             # w = b - w
+            be.multi_dot(w.view(1, -1), 1, w, nb)
+            beta = float(np.sqrt(max(nb[:1].cpu().numpy()[0].real, 0.0)))
+            rel = beta / bnorm
+            if rel <= rtol:
+                break
+            be.scale_copy(w, V[0], alpha=1.0 / beta)
+        else:
+            be.scale_copy(b, V[0], alpha=1.0 / beta)
+            first = False
+        H = np.zeros((m + 1, m), complex)
+        g = np.zeros(m + 1, complex)
+        g[0] = beta
+        cs = np.zeros(m, complex)
+        sn = np.zeros(m, complex)
+        j_used = 0
+        for j in range(m):
+            if precond is not None:
+                precond(V[j], z)
+                apply_A(z, w)
+            else:
+                apply_A(V[j], w)
+            h, hb = basis.orthogonalize(j)
+            total += 1
+            col = np.zeros(j + 2, complex)
+            col[:j + 1] = h
+            col[j + 1] = hb
+            for i in range(j):
+                t = cs[i] * col[i] + sn[i] * col[i + 1]
+                col[i + 1] = -np.conj(sn[i]) * col[i] + cs[i] * col[i + 1]
+                col[i] = t
+            a, bb = col[j], col[j + 1]
+            den = np.sqrt(abs(a) ** 2 + abs(bb) ** 2)
+            if den == 0.0:
+                cs[j], sn[j] = 1.0, 0.0
+            else:
+                cs[j] = abs(a) / den if a != 0 else 0.0
+                sn[j] = (a / abs(a)) * np.conj(bb) / den if a != 0 else 1.0
+            col[j] = cs[j] * a + sn[j] * bb
+            col[j + 1] = 0.0
+            g[j + 1] = -np.conj(sn[j]) * g[j]
+            g[j] = cs[j] * g[j]
+            H[:j + 2, j] = col
+            j_used = j + 1
+            rel = abs(g[j + 1]) / bnorm
+            if rel <= rtol or total >= maxiter or hb <= 1e-300:
+                break
+        y = np.linalg.solve(np.triu(H[:j_used, :j_used]), g[:j_used])
+        # x += M^{-1} (V y)
+        yd = be.asarray(-y, dtype=c128)
+        w.zero_()
+        be.multi_axpy(V, j_used, yd, w)
+        if precond is not None:
+            precond(w, z)
+            be.axpby(1.0, z, 1.0, x)
+        else:
+            be.axpby(1.0, w, 1.0, x)
+        if rel <= rtol:
+            break
+    return total, rel
+
+
+def _reorder_schur(T, Z, order_key):
+    """Reorder a complex Schur form so that diag(T) is sorted by order_key (descending)
+    using adjacent Givens swaps (complex upper-triangular => always well defined)."""
+    n = T.shape[0]
+    T = T.copy(); Z = Z.copy()
+    for i in range(n):
+        # bring the best remaining eigenvalue to position i (bubble up)
+        d = np.diag(T)
+        j = i + int(np.argmax(order_key(d[i:])))
+        for k in range(j - 1, i - 1, -1):
+            a, b, c = T[k, k], T[k, k + 1], T[k + 1, k + 1]
+            # Givens G with G^H [b; c-a] -> first column aligned so that T[k,k] <- c
+            x = np.array([b, c - a])
+            nx = np.linalg.norm(x)
+            if nx == 0.0:
+                continue
+            cgs, sgs = x[0] / nx, x[1] / nx
+            G = np.array([[cgs, -np.conj(sgs)], [sgs, np.conj(cgs)]])
+            T[:, k:k + 2] = T[:, k:k + 2] @ G
+            T[k:k + 2, :] = G.conj().T @ T[k:k + 2, :]
+            Z[:, k:k + 2] = Z[:, k:k + 2] @ G
+            T[k + 1, k] = 0.0
+    return T, Z
+
+
+def _triu_eigvecs(R):
+    """Unit-norm eigenvectors of an upper-triangular matrix (back substitution)."""
+    n = R.shape[0]
+    Y = np.zeros((n, n), complex)
+    small = np.finfo(float).eps * max(np.abs(R).max(), 1e-300)
+    for i in range(n):
+        y = np.zeros(n, complex)
+        y[i] = 1.0
+        for k in range(i - 1, -1, -1):
+            d = R[k, k] - R[i, i]
+            if abs(d) < small:
+                d = small
+            y[k] = -(R[k, k + 1:i + 1] @ y[k + 1:i + 1]) / d
+        Y[:, i] = y / np.linalg.norm(y)
+    return Y
+
+
+class KrylovSchurResult:
+    def __init__(self, theta, X, its, nconv, residuals, n_apply):
+        self.theta, self.X, self.its, self.nconv, self.residuals, self.n_apply = theta, X, its, nconv, residuals, n_apply
+
+
+def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, seed=0):
+    """nev eigenpairs of largest |theta| of the operator apply_op(v, out) on C^n.
+    SLEPc defaults: ncv = max(2 nev, nev+15) (eigensolvers.py:58 passes DECIDE),
+    restart keeping half of the non-converged part."""
+    import scipy.linalg as sla
+    if ncv is None:
+        ncv = max(2 * nev, nev + 15)
+    m = min(ncv, n - 1) if n > 2 else 1
+    basis = ArnoldiBasis(be, n, m)
+    V, w = basis.V, basis.w
+    if v0 is None:
+        g = torch.Generator().manual_seed(seed)
+        v0 = torch.randn(n, dtype=torch.float64, generator=g).to(c128)
+    v0 = be.asarray(v0, dtype=c128)
+    nb = be.zeros(2)
+    be.multi_dot(v0.view(1, -1), 1, v0, nb)
+    be.scale_copy(v0, V[0], alpha=1.0 / float(np.sqrt(nb[:1].cpu().numpy()[0].real)))
+    H = np.zeros((m + 1, m), complex)
+    k = 0
+    its = 0
+    n_apply = 0
+    Vnew = None
+    while True:
+        its += 1
+        mm = m
+        for j in range(k, m):
+            apply_op(V[j], w)
+            n_apply += 1
+            h, hb = basis.orthogonalize(j)
+            H[:j + 1, j] = h
+            H[j + 1, j] = hb
+            if hb <= 1e-14 * max(np.abs(h).max(), 1e-300):
+                mm = j + 1        # invariant subspace found
+                break
+        T, Z = sla.schur(H[:mm, :mm], output="complex")
+        T, Z = _reorder_schur(T, Z, np.abs)
+        bt = H[mm, :mm] @ Z if mm == m or True else None
+        bt = H[mm, :mm] @ Z
+        Y = _triu_eigvecs(T)
+        theta = np.diag(T).copy()
+        res = np.abs(bt @ Y)
+        nconv = 0
+        while nconv < mm and res[nconv] <= tol * abs(theta[nconv]):
+            nconv += 1
+        if nconv >= nev or its >= maxit or mm < m:
+            break
+        keep = min(max(nconv + (m - nconv) // 2, nev), m - 1)
+        if Vnew is None:
+            Vnew = be.zeros(m + 1, n)
+        Q = be.asarray(np.ascontiguousarray(Z[:, :keep].T), dtype=c128)      # (keep, m)
+        be.basis_rotate(V, m, Q, keep, Vnew)
+        Vnew[keep].copy_(V[m])
+        V[:keep + 1].copy_(Vnew[:keep + 1])
+        H[:] = 0.0
+        H[:keep, :keep] = T[:keep, :keep]
+        H[keep, :keep] = bt[:keep]
+        k = keep
+    nout = min(max(nev, nconv), mm)
+    # Ritz vectors X = V Z Y
+    ZY = Z @ Y[:, :nout]
+    X = be.zeros(nout, n)
+    Q = be.asarray(np.ascontiguousarray(ZY.T), dtype=c128)
+    be.basis_rotate(V, mm, Q, nout, X)
+    return KrylovSchurResult(theta[:nout], X, its, nconv, res[:nout], n_apply)

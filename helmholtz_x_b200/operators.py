@@ -1,0 +1,301 @@
+"""Matrix objects handed across the helmholtz_x API and the shifted inner solve.
+
+The reference passes PETSc ``Mat`` handles around and builds new matrices with
+``A + omega*B - D`` (helmholtz_x/eigensolvers.py:173-176,240,309-315).  Here a ``Mat`` is
+a *symbolic* linear combination of the assembled base operators A, B, B^H, C that
+share one CSR pattern, plus optional rank-r flame terms kept as sparse vectors
+(never densified): the same expressions work, nothing is re-assembled, and the
+shift-invert solve sees the structure it needs (multigrid on the sparse part,
+Woodbury for the low-rank part).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import krylov
+from .amg import AMG
+from .backend import LowRank
+from .fem import _Vec
+
+c128 = torch.complex128
+f64 = torch.float64
+
+BASES = ("A", "B", "Bh", "C")
+
+
+def build_lowrank(be, n, left_list, right_list) -> LowRank:
+    """left_list / right_list: per flame (idx int array, val float array), host numpy."""
+    r = len(left_list)
+    rptr = np.zeros(r + 1, np.int32)
+    for f, (idx, _) in enumerate(right_list):
+        rptr[f + 1] = rptr[f] + len(idx)
+    ridx = np.concatenate([np.asarray(i, np.int32) for i, _ in right_list]) if r else np.zeros(0, np.int32)
+    rval = np.concatenate([np.asarray(v, np.float64) for _, v in right_list]) if r else np.zeros(0)
+    rows = np.concatenate([np.asarray(i, np.int64) for i, _ in left_list]) if r else np.zeros(0, np.int64)
+    cols = np.concatenate([np.full(len(i), f, np.int32) for f, (i, _) in enumerate(left_list)]) if r else np.zeros(0, np.int32)
+    vals = np.concatenate([np.asarray(v, np.float64) for _, v in left_list]) if r else np.zeros(0)
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    lrow, start = np.unique(rows, return_index=True)
+    lptr = np.append(start, len(rows)).astype(np.int32)
+    a = be.asarray
+    return LowRank(n, r, a(rptr, dtype=torch.int32), a(ridx, dtype=torch.int32), a(rval, dtype=f64),
+                   a(lrow.astype(np.int32), dtype=torch.int32), a(lptr, dtype=torch.int32), a(cols, dtype=torch.int32),
+                   a(vals, dtype=f64))
+
+
+class LowRankMat:
+    """coef * sum_f left_f right_f^T  (what FlameMatrix.matrix returns)."""
+
+    def __init__(self, n, lr: LowRank, lr_T: LowRank, coef=1.0, lists=None):
+        self.n, self.lr, self.lr_T, self.coef, self.lists = n, lr, lr_T, complex(coef), lists
+
+    def __mul__(self, z):
+        return LowRankMat(self.n, self.lr, self.lr_T, self.coef * complex(z), self.lists)
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return self * -1.0
+
+    def transpose(self):
+        return LowRankMat(self.n, self.lr_T, self.lr, self.coef, None if self.lists is None else self.lists[::-1])
+
+    def getSize(self):
+        return (self.n, self.n)
+
+    def dense_block_nnz(self):
+        l, r = self.lists
+        return int(sum(len(a[0]) * len(b[0]) for a, b in zip(l, r)))
+
+    def to_scipy(self):
+        """Densified D_ij as SciPy CSR (tests only; the product never forms it)."""
+        import scipy.sparse as sp
+        l, r = self.lists
+        M = sp.csr_matrix((self.n, self.n), dtype=complex)
+        for (li, lv), (ri, rv) in zip(l, r):
+            M = M + sp.csr_matrix((np.outer(lv, rv).ravel(), (np.repeat(li, len(ri)), np.tile(ri, len(li)))),
+                                  shape=(self.n, self.n))
+        return self.coef * M
+
+
+class Mat:
+    """sum_k terms[k] * base_k  +  sum (LowRankMat)   on one OperatorSet."""
+
+    def __init__(self, ops, terms, lowrank=()):
+        self.ops = ops
+        self.terms = {k: complex(v) for k, v in terms.items() if v != 0}
+        self.lowrank = tuple(lowrank)
+
+    # -- algebra ---------------------------------------------------------------------------
+    def __mul__(self, z):
+        z = complex(z)
+        return Mat(self.ops, {k: v * z for k, v in self.terms.items()}, [m * z for m in self.lowrank])
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return self * -1.0
+
+    def __add__(self, other):
+        if isinstance(other, LowRankMat):
+            return Mat(self.ops, self.terms, self.lowrank + (other,))
+        if other is None or (np.isscalar(other) and other == 0):
+            return self
+        if not isinstance(other, Mat) or other.ops is not self.ops:
+            raise TypeError("Mat + Mat needs operands assembled on the same AcousticMatrices")
+        t = dict(self.terms)
+        for k, v in other.terms.items():
+            t[k] = t.get(k, 0) + v
+        return Mat(self.ops, t, self.lowrank + other.lowrank)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self + (-other)
+
+    def __bool__(self):
+        return True
+
+    def copy(self):
+        return Mat(self.ops, self.terms, self.lowrank)
+
+    def hermitian_transpose(self):
+        """conj-transpose: A, C real symmetric; B complex symmetric => B^H = conj(B)."""
+        sw = {"A": "A", "C": "C", "B": "Bh", "Bh": "B"}
+        return Mat(self.ops, {sw[k]: np.conj(v) for k, v in self.terms.items()},
+                   [LowRankMat(m.n, m.lr_T, m.lr, np.conj(m.coef), None if m.lists is None else m.lists[::-1])
+                    for m in self.lowrank])
+
+    # -- PETSc-like surface used by drivers / eigenvectors.py --------------------------------------
+    def getSize(self):
+        return (self.ops.n, self.ops.n)
+
+    def createVecs(self):
+        return _Vec(np.zeros(self.ops.n, complex)), _Vec(np.zeros(self.ops.n, complex))
+
+    getVecs = createVecs
+
+    def values(self):
+        return self.ops.combine(self.terms)
+
+    def csr(self):
+        return self.ops.space.matrix(self.values())
+
+    def getValuesCSR(self):
+        indptr, indices = self.ops.space.pattern()
+        return indptr.cpu().numpy(), indices.cpu().numpy(), self.values().cpu().numpy()
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        ip, ix, v = self.getValuesCSR()
+        M = sp.csr_matrix((v, ix, ip), shape=self.getSize())
+        for lr in self.lowrank:
+            M = M + lr.to_scipy()
+        return M
+
+    def apply(self, x, y):
+        """y = self @ x on device tensors (sparse part by SpMV, flame part matrix-free)."""
+        be = self.ops.be
+        be.spmv(self.csr(), x, y)
+        for m in self.lowrank:
+            t = be.zeros(max(m.lr.r, 1))
+            be.lowrank_dots(m.lr, x, t)
+            be.lowrank_update(m.lr, t, m.coef, y)
+        return y
+
+    def mult(self, x, y):
+        """PETSc MatMult on host Vec wrappers (petsc4py_utils.py:86,96)."""
+        be = self.ops.be
+        xd = be.asarray(np.asarray(x.array, complex), dtype=c128)
+        yd = be.zeros(self.ops.n)
+        self.apply(xd, yd)
+        y.setArray(yd.cpu().numpy())
+
+
+class OperatorSet:
+    """Base operators of one AcousticMatrices on the device + the multigrid hierarchy."""
+
+    def __init__(self, space, a_vals, c_vals, b_vals=None):
+        self.space, self.be, self.n = space, space.be, space.n
+        self.base = {"A": a_vals, "C": c_vals, "B": b_vals, "Bh": torch.conj_physical(b_vals) if b_vals is not None else None}
+        self._amg = None
+        self._cache = {}
+        self.amg_options = {}
+        self.stats = {"inner_solves": 0, "inner_iterations": 0, "amg_setups": 0, "shifts": 0}
+
+    def combine(self, terms):
+        key = tuple(sorted(terms.items()))
+        if key not in self._cache:
+            if len(self._cache) > 8:
+                self._cache.clear()
+            out = self.be.empty(self.space.pattern()[1].numel())
+            t = dict(terms)
+            if t.get("B", 0) != 0 and t.get("Bh", 0) != 0:
+                raise ValueError("B and B^H cannot be combined in one operator")
+            b, cb = (self.base["Bh"], t.get("Bh")) if t.get("Bh", 0) != 0 else (self.base["B"], t.get("B", 0))
+            if cb and b is None:
+                raise ValueError("operator has no B matrix")
+            self.be.combine_abc(self.base["A"], b if cb else None, self.base["C"], t.get("A", 0), cb or 0, t.get("C", 0), out)
+            self._cache[key] = out
+        return self._cache[key]
+
+    def amg(self):
+        if self._amg is None:
+            pat = self.space.matrix
+            B = pat(self.base["B"]) if self.base["B"] is not None else None
+            self._amg = AMG(self.be, pat(self.base["A"]), pat(self.base["C"]), B, self.space.dof_coords, **self.amg_options)
+            self.stats["amg_setups"] += 1
+        return self._amg
+
+
+class ShiftedSolver:
+    """x = (P + sum coef_k L_k R_k^T)^{-1} b,  P = sum terms*base  -- GMRES preconditioned
+    by the SA-AMG V-cycle for P, Woodbury for the flame terms (hard part 2)."""
+
+    def __init__(self, ops: OperatorSet, terms, lowrank=(), rtol=1e-11, restart=40, maxiter=400, transposed=False):
+        self.ops, self.be = ops, ops.be
+        be = self.be
+        self.rtol, self.restart, self.maxiter = rtol, restart, maxiter
+        t = dict(terms)
+        use_bh = t.get("Bh", 0) != 0
+        self.P_values = ops.combine(t)
+        self.P = ops.space.matrix(self.P_values)
+        mg = ops.amg()
+        if use_bh:
+            # coarse B^H = conj(B_c): run the hierarchy on conjugated B
+            for L in mg.levels:
+                if L.b is not None and not hasattr(L, "b_direct"):
+                    L.b_direct = L.b
+                    L.b_conj = torch.conj_physical(L.b)
+            for L in mg.levels:
+                if L.b is not None:
+                    L.b = L.b_conj
+            mg.set_shift(t.get("A", 0), t.get("Bh", 0), t.get("C", 0), fine_values=self.P_values)
+            for L in mg.levels:
+                if L.b is not None:
+                    L.b = L.b_direct
+        else:
+            mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=self.P_values)
+        self.mg = mg
+        ops.stats["shifts"] += 1
+        n = ops.n
+        self.basis = krylov.ArnoldiBasis(be, n, restart)
+        self.work = be.zeros(n)
+        self.lowrank = [m for m in lowrank if m.coef != 0 and m.lr.r > 0]
+        if transposed:
+            self.lowrank = [m.transpose() for m in self.lowrank]
+        self.Z = []
+        if self.lowrank:
+            self._setup_woodbury()
+
+    def _solve_P(self, b, x):
+        its, rel = krylov.gmres(self.be, lambda v, o: self.be.spmv(self.P, v, o), b, x, precond=self.mg.apply,
+                                rtol=self.rtol, restart=self.restart, maxiter=self.maxiter, basis=self.basis, work=self.work)
+        self.ops.stats["inner_solves"] += 1
+        self.ops.stats["inner_iterations"] += its
+        if rel > max(self.rtol * 100, 1e-8):
+            raise RuntimeError(f"inner GMRES stagnated: rel. residual {rel:.2e} after {its} iterations")
+        return x
+
+    def _setup_woodbury(self):
+        """(P - U W^T)^-1 with U = -coef*L (n x r dense), W = R: Z = P^-1 U, S = I - W^T Z."""
+        be, n = self.be, self.ops.n
+        r_tot = sum(m.lr.r for m in self.lowrank)
+        self.Zmat = be.zeros(r_tot, n)
+        u = be.zeros(n)
+        col = 0
+        for m in self.lowrank:
+            for f in range(m.lr.r):
+                u.zero_()
+                e = be.zeros(m.lr.r)
+                e[f] = 1.0
+                be.lowrank_update(m.lr, e, -m.coef, u)          # u = -coef * left_f
+                self._solve_P(u, self.Zmat[col])
+                col += 1
+        S = np.eye(r_tot, dtype=complex)
+        row = 0
+        t = be.zeros(max(max(m.lr.r for m in self.lowrank), 1))
+        for m in self.lowrank:
+            for cz in range(r_tot):
+                be.lowrank_dots(m.lr, self.Zmat[cz], t)
+                S[row:row + m.lr.r, cz] -= t[:m.lr.r].cpu().numpy()
+            row += m.lr.r
+        self.S_inv = np.linalg.inv(S)
+        self.r_tot = r_tot
+        self._t = t
+
+    def solve(self, b, x):
+        self._solve_P(b, x)
+        if self.lowrank:
+            be = self.be
+            wt = np.zeros(self.r_tot, complex)
+            row = 0
+            for m in self.lowrank:
+                be.lowrank_dots(m.lr, x, self._t)
+                wt[row:row + m.lr.r] = self._t[:m.lr.r].cpu().numpy()
+                row += m.lr.r
+            cvec = self.S_inv @ wt
+            be.multi_axpy(self.Zmat, self.r_tot, be.asarray(-cvec, dtype=c128), x)
+        return x

@@ -1,0 +1,142 @@
+"""Host-side logic of the product (Krylov-Schur, GMRES, AMG cycle order, Woodbury flame
+term, fixed-point recurrences) on the CPU test double -- no GPU, no CUDA kernels."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+import torch
+
+from helmholtz_x_b200 import eigensolvers, krylov
+from oracle import hx_oracle as ox
+from oracle.host_backend import HostBackend
+from tests import cases
+from tests.host_helpers import HostFlame, HostOperators
+
+G = cases.golden_values()
+
+
+@pytest.fixture(scope="module")
+def rijke():
+    case = cases.rijke3d()
+    return case, HostOperators(case)
+
+
+def test_krylov_schur_matches_passive_golden(rijke):
+    """numerical_examples/Longitudinal/NetworkCode/RijkeTube3D/Results/Passive/passive.log:30-33"""
+    case, _ = rijke
+    hops = HostOperators(case, passive=True)
+    E = eigensolvers.eps_solver(hops.A, hops.C, case.target, nev=2)
+    lam = np.sort_complex(np.array([E.getEigenvalue(i) for i in range(2)]))
+    gold = np.array(G["rijke3d_passive_eps"]["lambdas"])
+    assert abs(lam[1] - gold[0]) / gold[0] < 1e-9
+    assert abs(lam[0]) < 1e-3      # the null (constant) mode
+
+
+def test_krylov_schur_restart_path():
+    rng = np.random.default_rng(1)
+    n = 300
+    d = np.concatenate([[50, 40, 30, 20], rng.uniform(0.1, 5, n - 4)]) * np.exp(1j * rng.uniform(0, 0.3, n))
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    Mx = (Q * d) @ Q.conj().T
+    be = HostBackend()
+    res = krylov.krylov_schur(be, lambda v, o: o.copy_(torch.from_numpy(Mx @ v.numpy())), n, nev=4, ncv=10, tol=1e-12)
+    assert res.its > 1 and res.nconv >= 4
+    assert np.allclose(np.sort_complex(res.theta[:4]), np.sort_complex(d[:4]), rtol=1e-10)
+    for i in range(4):
+        x = res.X[i].numpy()
+        assert np.linalg.norm(Mx @ x - res.theta[i] * x) < 1e-8 * abs(res.theta[i])
+
+
+def test_gmres_restarts_and_true_residual(rijke):
+    _, hops = rijke
+    be = hops.ops.be
+    P = hops.ops.space.matrix(hops.ops.combine({"A": 1.0, "C": (400 * np.pi) ** 2}))
+    Ps = P.to_scipy()
+    ilu = spla.spilu(Ps.tocsc(), drop_tol=1e-2, fill_factor=2)
+    b = torch.randn(P.n_rows, dtype=torch.float64, generator=torch.Generator().manual_seed(0)).to(torch.complex128)
+    x = torch.zeros_like(b)
+    its, rel = krylov.gmres(be, lambda v, o: be.spmv(P, v, o), b, x, rtol=1e-10, restart=30, maxiter=400,
+                            precond=lambda v, o: o.copy_(torch.from_numpy(ilu.solve(v.numpy()))))
+    assert 30 < its < 400, "restart path not exercised / stagnation"
+    assert np.linalg.norm(Ps @ x.numpy() - b.numpy()) / np.linalg.norm(b.numpy()) < 2e-10
+
+
+def test_amg_preconditioned_solve(rijke):
+    _, hops = rijke
+    mg = hops.ops.amg()
+    assert mg.sizes[0] == 2426 and len(mg.sizes) >= 2
+    from helmholtz_x_b200.operators import ShiftedSolver
+    s = ShiftedSolver(hops.ops, {"A": 1.0, "C": (400 * np.pi) ** 2}, rtol=1e-11)
+    b = torch.ones(hops.ops.n, dtype=torch.complex128)
+    x = torch.zeros_like(b)
+    s.solve(b, x)
+    Ps = s.P.to_scipy()
+    assert np.linalg.norm(Ps @ x.numpy() - b.numpy()) / np.linalg.norm(b.numpy()) < 1e-10
+    assert hops.ops.stats["inner_iterations"] < 40
+
+
+def test_woodbury_flame_term_matches_densified(rijke):
+    case, hops = rijke
+    D = HostFlame(case, hops)
+    om = 1248.5 + 3.4j
+    D.assemble_matrix(om)
+    K = hops.A - D.matrix
+    from helmholtz_x_b200.operators import ShiftedSolver
+    terms = {"A": 1.0, "C": (400 * np.pi) ** 2}
+    s = ShiftedSolver(hops.ops, terms, K.lowrank, rtol=1e-12)
+    b = torch.randn(hops.ops.n, dtype=torch.float64, generator=torch.Generator().manual_seed(2)).to(torch.complex128)
+    x = torch.zeros_like(b)
+    s.solve(b, x)
+    dense = (K.to_scipy() + (400 * np.pi) ** 2 * hops.C.to_scipy()).tocsc()      # densified reference operator
+    ref = spla.spsolve(dense, b.numpy())
+    assert np.linalg.norm(x.numpy() - ref) / np.linalg.norm(ref) < 1e-8
+    # matrix-free apply == densified apply
+    y = torch.zeros_like(b)
+    K.apply(b, y)
+    assert np.allclose(y.numpy(), K.to_scipy() @ b.numpy(), rtol=1e-12, atol=1e-9)
+
+
+def test_fpi_eps_matches_golden_log(rijke, capsys):
+    """config 1: .../RijkeTube3D/Results/Active/active.log:23-52 through the product's
+    fixed_point_iteration (host logic) on the CPU double."""
+    case, hops = rijke
+    D = HostFlame(case, hops)
+    E = eigensolvers.fixed_point_iteration(hops, D, case.target, nev=2, i=0, tol=1e-8)
+    gold = [cases.cplx(p) for p in G["rijke3d_active_fpi"]["omegas"]]
+    hist = E.omega_history
+    assert len(hist) == len(gold)
+    for a, b in zip(hist, gold):
+        assert abs(a - b) < 2e-8 * abs(b) + 1e-8
+    out = capsys.readouterr().out
+    assert "+ Starting eigenvalue is found: +1249.66494052  +0.00000000j." in out
+    assert "* iter =  4" in out
+
+
+def test_fpi_pep_direct_and_adjoint_match_golden():
+    """PRF Rijke3D (Robin, PEP): .../PRF/RijkeTube3D/Results/Active/active.log:21-50,57-86"""
+    case = cases.prf_rijke3d()
+    hops = HostOperators(case)
+    D = HostFlame(case, hops)
+    E = eigensolvers.fixed_point_iteration(hops, D, case.target, nev=2, i=0)
+    gold = [cases.cplx(p) for p in G["prf_rijke3d_direct_fpi"]["omegas"]]
+    for a, b in zip(E.omega_history[1:], gold):
+        assert abs(a - b) < 2e-8
+    E2 = eigensolvers.fixed_point_iteration(hops, D, case.target, nev=2, i=0, problem_type='adjoint')
+    gold = [cases.cplx(p) for p in G["prf_rijke3d_adjoint_fpi"]["omegas"]]
+    for a, b in zip(E2.omega_history[1:], gold):
+        assert abs(a - b) < 2e-8
+
+
+def test_two_sided_left_vectors(rijke):
+    case, hops = rijke
+    D = HostFlame(case, hops)
+    om = 1247.4 + 6.8j
+    D.assemble_matrix(om)
+    L = hops.A + om ** 2 * hops.C - D.matrix
+    E = eigensolvers.eps_solver(L, -hops.C, 0, 2, two_sided=True)
+    Ls, Cs = L.to_scipy(), hops.C.to_scipy()
+    lam = E.getEigenvalue(0)
+    y = E.device_vector(0, "left").numpy()
+    x = E.device_vector(0, "right").numpy()
+    assert np.linalg.norm(Ls @ x - lam * (Cs @ x)) < 1e-7 * np.linalg.norm(Ls @ x)
+    r = y.conj() @ Ls - lam * (y.conj() @ Cs)
+    assert np.linalg.norm(r) < 1e-7 * np.linalg.norm(y.conj() @ Ls)
