@@ -140,6 +140,24 @@ def tet_rule_deg2():
     return L, np.full(4, 0.25)
 
 
+def tet_rule_deg5_14():
+    """14-point degree-5 rule (Walkington/Keast); the rule the CUDA path uses for the
+    non-polynomial P2 right flame vector.  Weights sum to 1."""
+    a1, w1 = 0.31088591926330060980, 0.11268792571801585080
+    a2, w2 = 0.092735250310891226402, 0.073493043116361949544
+    b3, w3 = 0.045503704125649649492, 0.042546020777081466438
+    L, w = [], []
+    for a, ww in ((a1, w1), (a2, w2)):
+        for i in range(4):
+            p = [a] * 4; p[i] = 1 - 3 * a
+            L.append(p); w.append(ww)
+    for i in range(4):
+        for j in range(i + 1, 4):
+            p = [0.5 - b3] * 4; p[i] = b3; p[j] = b3
+            L.append(p); w.append(w3)
+    return np.array(L), np.array(w)
+
+
 def reference_tensors(degree):
     """Exact reference integrals (unit-volume scaling) used by the assembly.
 
@@ -585,8 +603,8 @@ def distributed_flame(mesh, w, h, rho, T, q_0, u_b, FTF, degree=1, gamma=None, t
     left_i  = int (gamma-1) q0/u_b h phi_i dx            (:199)
     right_j = int (e_z . grad phi_j) w / rho dx          (:200)
     The right integrand is not polynomial: FFCx estimates degree 2 (P1) / 3 (P2);
-    P1 uses the 4-point degree-2 rule (pinned by goldens), P2 a higher GJ rule
-    (unpinned, sensitivity ~1e-10 rel. in omega)."""
+    P1 uses the 4-point degree-2 rule (pinned by goldens), P2 the 14-point degree-5
+    rule (unpinned, sensitivity ~1e-10 rel. in omega)."""
     space = function_space(mesh, degree)
     vol, G = geometry(mesh)
     ref = reference_tensors(degree)
@@ -603,7 +621,7 @@ def distributed_flame(mesh, w, h, rho, T, q_0, u_b, FTF, degree=1, gamma=None, t
     if degree == 1:
         Lq, wq = tet_rule_deg2()
     else:
-        Lq, wq = tet_rule(4)
+        Lq, wq = tet_rule_deg5_14()
     _, d = tabulate(degree, Lq)
     wq_rho = (w[cells] @ Lq.T) / (rho[cells] @ Lq.T)                # (nc,nq)
     dz = np.einsum("qak,ck->cqa", d, G[:, :, 2])                     # d phi_a/dz at q

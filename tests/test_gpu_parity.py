@@ -1,0 +1,447 @@
+"""GPU parity tests: every product call goes through libhx_b200.so (the C-ABI) and is
+compared with the CPU oracle on the same inputs, and with the reference's golden
+logs where one exists.  Bars: bit-exact for integer/index work (CSR pattern, dof
+maps, point ownership); relative 1e-12 for assembled FP64 values; relative 1e-8 for
+eigenvalues (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hx_oracle as ox
+from tests import cases
+from tests.gpu_helpers import gpu_flame, gpu_mesh, gpu_operators
+
+pytestmark = pytest.mark.gpu
+
+G = cases.golden_values()
+VAL_RTOL = 1e-12     # assembled values, relative to the largest entry
+EIG_RTOL = 1e-8      # eigenvalue parity (north star)
+
+
+def be():
+    from helmholtz_x_b200.fem import default_backend
+    return default_backend()
+
+
+def relmax(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def on_pattern(space, Mx):
+    return ox._on_pattern(space, Mx)
+
+
+CASES = {"rijke3d": cases.rijke3d, "prf": cases.prf_rijke3d, "rijkeffd": cases.rijkeffd, "annulus": cases.annulus}
+
+
+def degree_case(name, degree):
+    c = CASES[name]()
+    c["degree"] = degree
+    return c
+
+
+# ---------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("name,degree", [("rijke3d", 1), ("rijke3d", 2), ("annulus", 1)])
+def test_csr_pattern_and_dofmap_bit_exact(name, degree):
+    from helmholtz_x_b200 import fem
+    case = degree_case(name, degree)
+    V = fem.functionspace(gpu_mesh(case), ("Lagrange", degree))
+    sp_ = ox.function_space(case.mesh, degree)
+    assert V.n == sp_.n
+    assert np.array_equal(V.cell_dofs.cpu().numpy(), sp_.cell_dofs)
+    assert np.array_equal(V.facet_dofs.cpu().numpy(), sp_.facet_dofs)
+    indptr, indices = V.pattern()
+    ip, ix = ox.csr_pattern(sp_)
+    assert np.array_equal(indptr.cpu().numpy(), ip)
+    assert np.array_equal(indices.cpu().numpy(), ix)
+
+
+def test_pattern_is_run_to_run_deterministic():
+    from helmholtz_x_b200 import fem
+    case = cases.rijke3d()
+    m = gpu_mesh(case)
+    a = fem.FunctionSpace(m, 2).pattern()
+    b = fem.FunctionSpace(m, 2).pattern()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ---------------------------------------------------------------------------- K1-K3
+@pytest.mark.parametrize("name,degree", [("rijke3d", 1), ("prf", 1), ("rijkeffd", 1), ("annulus", 1), ("prf", 2),
+                                         ("annulus", 2)])
+def test_assembled_A_B_C_match_oracle(name, degree):
+    case = degree_case(name, degree)
+    mats = gpu_operators(case)
+    ops = cases.oracle_operators(case)
+    sp_ = ops.space
+    a = mats.ops.base["A"].cpu().numpy()
+    c = mats.ops.base["C"].cpu().numpy()
+    assert relmax(a, on_pattern(sp_, ops.A).real) < VAL_RTOL
+    assert relmax(c, on_pattern(sp_, ops.C).real) < VAL_RTOL
+    if ops.B is None:
+        assert mats.B is None
+    else:
+        b = mats.ops.base["B"].cpu().numpy()
+        assert relmax(b, on_pattern(sp_, ops.B)) < VAL_RTOL
+        ip, ix, v = mats.B_adj.getValuesCSR()
+        assert relmax(v, on_pattern(sp_, ops.B_adj)) < VAL_RTOL
+
+
+def test_assembly_is_bitwise_reproducible():
+    from helmholtz_x_b200 import fem
+    case = degree_case("prf", 2)
+    V = fem.functionspace(gpu_mesh(case), ("Lagrange", 2))
+    a1, c1 = fem.assemble_AC(V, case.c)
+    a2, c2 = fem.assemble_AC(V, case.c)
+    assert torch.equal(a1, a2) and torch.equal(c1, c2)
+
+
+def test_dirichlet_rows_cols_and_unit_diagonal():
+    case = cases.rijke3d()
+    case["bcs"] = {1: {"Dirichlet"}, 2: {"Neumann"}, 3: {"Neumann"}}
+    mats = gpu_operators(case)
+    ops = cases.oracle_operators(case)
+    assert relmax(mats.ops.base["A"].cpu().numpy(), on_pattern(ops.space, ops.A).real) < VAL_RTOL
+    assert relmax(mats.ops.base["C"].cpu().numpy(), on_pattern(ops.space, ops.C).real) < VAL_RTOL
+
+
+def test_choked_boundaries_match_oracle():
+    """ChokedInlet/ChokedOutlet with T-dependent gamma (acoustic_matrices.py:75-97) on the Rijke mesh."""
+    case = cases.rijkeffd()
+    case["bcs"] = {1: {"Neumann"}, 2: {"ChokedOutlet": 0.05}, 3: {"ChokedInlet": 0.02}}
+    mats = gpu_operators(case)
+    ops = cases.oracle_operators(case)
+    assert relmax(mats.ops.base["B"].cpu().numpy(), on_pattern(ops.space, ops.B)) < 1e-11
+
+
+# ---------------------------------------------------------------------------- K5/K6
+@pytest.mark.parametrize("name,degree", [("rijke3d", 1), ("rijkeffd", 1), ("rijke3d", 2)])
+def test_distributed_flame_vectors(name, degree):
+    case = degree_case(name, degree)
+    D = gpu_flame(case)
+    D.assemble_submatrices()
+    fl = cases.oracle_flame(case)
+    (li, lv), = D.submatrices.lists[0]
+    (ri, rv), = D.submatrices.lists[1]
+    ol, orr = fl.left[:, 0], fl.right[:, 0]
+    # thresholding near tol may flip single entries; compare dense vectors
+    dl = np.zeros_like(ol); dl[li] = lv
+    dr = np.zeros_like(orr); dr[ri] = rv
+    assert np.abs(dl - ol).max() < 1e-12 * np.abs(ol).max() + 2e-5 * (np.count_nonzero(dl) != np.count_nonzero(ol))
+    assert np.abs(dr - orr).max() < 1e-12 * np.abs(orr).max() + 2e-5 * (np.count_nonzero(dr) != np.count_nonzero(orr))
+    if degree == 1 and name == "rijke3d":
+        assert (len(li), len(ri)) == (558, 569)        # SURVEY K5 (reference block 558 x 569)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_pointwise_flame_vectors_and_point_ownership(degree):
+    case = degree_case("annulus", degree)
+    D = gpu_flame(case)
+    D.assemble_submatrices()
+    fl = cases.oracle_flame(case)
+    lefts, rights = D.submatrices.lists
+    assert len(lefts) == 16
+    for f in range(16):
+        dl = np.zeros(fl.left.shape[0]); dl[lefts[f][0]] = lefts[f][1]
+        dr = np.zeros(fl.left.shape[0]); dr[rights[f][0]] = rights[f][1]
+        assert np.abs(dl - fl.left[:, f]).max() < 1e-11 * np.abs(fl.left[:, f]).max()
+        assert np.abs(dr - fl.right[:, f]).max() < 1e-11 * np.abs(fl.right[:, f]).max()
+    if degree == 1:
+        assert D.submatrices.dense_block_nnz() == fl.dense_block_nnz()
+
+
+# ---------------------------------------------------------------------------- K7/K8
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
+def test_spmv_complex_csr_all_lane_widths(lanes):
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    s = case.target
+    P = (mats.A + s * mats.B + s ** 2 * mats.C)
+    csr = P.csr()
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(csr.n_cols) + 1j * rng.standard_normal(csr.n_cols)
+    xd = be().asarray(x, dtype=torch.complex128)
+    yd = be().zeros(csr.n_rows)
+    be().spmv(csr, xd, yd, lanes=lanes)
+    ref = ox.spmv(csr.indptr.cpu().numpy(), csr.indices.cpu().numpy(), csr.values.cpu().numpy(), x)
+    assert relmax(yd.cpu().numpy(), ref) < 1e-13
+    # alpha/beta form, real-valued matrix path
+    y0 = be().asarray(rng.standard_normal(csr.n_rows) + 0j, dtype=torch.complex128)
+    Cr = mats.ops.space.matrix(mats.ops.base["C"])
+    be().spmv(Cr, xd, yd, alpha=2 - 1j, beta=0.5j, y0=y0, lanes=lanes)
+    refc = (2 - 1j) * ox.spmv(Cr.indptr.cpu().numpy(), Cr.indices.cpu().numpy(), Cr.values.cpu().numpy(), x) + 0.5j * y0.cpu().numpy()
+    assert relmax(yd.cpu().numpy(), refc) < 1e-13
+
+
+def test_spmv_edge_cases_empty_rows_and_ragged():
+    from helmholtz_x_b200.backend import CsrMatrix
+    b = be()
+    indptr = np.array([0, 0, 3, 3, 4, 4 + 70], np.int32)       # empty rows, a long ragged row
+    rng = np.random.default_rng(3)
+    indices = np.concatenate([[0, 2, 4], [1], np.sort(rng.choice(100, 70, replace=False))]).astype(np.int32)
+    vals = rng.standard_normal(74) + 1j * rng.standard_normal(74)
+    x = rng.standard_normal(100) + 1j * rng.standard_normal(100)
+    M = CsrMatrix(5, 100, b.asarray(indptr), b.asarray(indices), b.asarray(vals, dtype=torch.complex128))
+    for lanes in (2, 8, 32):
+        y = b.zeros(5)
+        b.spmv(M, b.asarray(x, dtype=torch.complex128), y, lanes=lanes)
+        assert relmax(y.cpu().numpy(), ox.spmv(indptr, indices, vals, x)) < 1e-14
+    # n = 0 is a no-op
+    M0 = CsrMatrix(0, 100, b.asarray(np.zeros(1, np.int32)), b.asarray(np.zeros(0, np.int32)), b.zeros(0))
+    b.spmv(M0, b.asarray(x, dtype=torch.complex128), b.zeros(1))
+
+
+def test_spmv_sell_matches_csr():
+    from helmholtz_x_b200.sell import SellMatrix
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    s = case.target
+    csr = (mats.A + s * mats.B + s ** 2 * mats.C).csr()
+    sell = SellMatrix.from_csr(be(), csr)
+    rng = np.random.default_rng(1)
+    x = be().asarray(rng.standard_normal(csr.n_cols) + 1j * rng.standard_normal(csr.n_cols), dtype=torch.complex128)
+    y1, y2 = be().zeros(csr.n_rows), be().zeros(csr.n_rows)
+    be().spmv(csr, x, y1)
+    sell.spmv(x, y2)
+    assert relmax(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-13
+    assert sell.padding_ratio < 1.25
+
+
+def test_fused_operator_apply_with_flame_term():
+    case = cases.rijke3d()
+    mats = gpu_operators(case)
+    D = gpu_flame(case)
+    D.assemble_submatrices()
+    om = 1248.5 + 3.4j
+    D.assemble_matrix(om)
+    Lm = mats.A + om ** 2 * mats.C - D.matrix
+    ops = cases.oracle_operators(case)
+    fl = cases.oracle_flame(case)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(ops.A.shape[0]) + 1j * rng.standard_normal(ops.A.shape[0])
+    y = be().zeros(len(x))
+    Lm.apply(be().asarray(x, dtype=torch.complex128), y)
+    ref = ox.fused_apply(ops, fl, om, fl.FTF(om), x)
+    assert relmax(y.cpu().numpy(), ref) < 1e-12
+
+
+# ---------------------------------------------------------------------------- K10/K11
+def test_basis_kernels_match_numpy_and_are_deterministic():
+    b = be()
+    rng = np.random.default_rng(7)
+    n, m = 100003, 19
+    Vh = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    wh = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    V = b.asarray(Vh, dtype=torch.complex128)
+    w = b.asarray(wh, dtype=torch.complex128)
+    out = b.zeros(m + 2)
+    for k in (1, 7, 8, 9, 19):
+        b.multi_dot(V, k, w, out)
+        assert relmax(out[:k].cpu().numpy(), Vh[:k].conj() @ wh) < 1e-13
+        o1 = out[:k].clone()
+        b.multi_dot(V, k, w, out)
+        assert torch.equal(o1, out[:k]), "reduction is not run-to-run deterministic"
+        b.multi_dot(V, k, w, out, conj=False)
+        assert relmax(out[:k].cpu().numpy(), Vh[:k] @ wh) < 1e-13
+    h = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    hd = b.asarray(h, dtype=torch.complex128)
+    hacc = b.zeros(m + 2)
+    nr = torch.view_as_real(hacc)[m + 1]
+    w2 = w.clone()
+    b.multi_axpy(V, m, hd, w2, hacc=hacc, nrm2=nr)
+    ref = wh - h @ Vh
+    assert relmax(w2.cpu().numpy(), ref) < 1e-13
+    assert relmax(hacc[:m].cpu().numpy(), h) < 1e-15
+    assert abs(float(nr[0]) - np.vdot(ref, ref).real) < 1e-12 * np.vdot(ref, ref).real
+    o = b.zeros(n)
+    b.scale_copy(w2, o, nrm2=nr)
+    assert abs(np.linalg.norm(o.cpu().numpy()) - 1) < 1e-13
+    b.axpby(2j, w, -1.0, o)
+    Q = rng.standard_normal((11, m)) + 1j * rng.standard_normal((11, m))
+    Vout = b.zeros(11, n)
+    b.basis_rotate(V, m, b.asarray(Q, dtype=torch.complex128), 11, Vout)
+    assert relmax(Vout.cpu().numpy(), Q @ Vh) < 1e-13
+
+
+def test_dense_inverse_and_gemv():
+    b = be()
+    rng = np.random.default_rng(11)
+    for n in (1, 5, 64, 300):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        A[0, 0] = 0.0 if n > 1 else A[0, 0]          # force a pivot exchange
+        Acm = b.asarray(np.ascontiguousarray(A.T), dtype=torch.complex128)
+        info = b.dense_inverse(Acm)
+        assert int(info[0]) == 0
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        y = b.zeros(n)
+        b.dense_gemv(Acm, b.asarray(x, dtype=torch.complex128), y)
+        assert relmax(y.cpu().numpy(), np.linalg.solve(A, x)) < 1e-9
+
+
+def test_ilu0_level_scheduled_matches_host_ilu0():
+    from helmholtz_x_b200.ilu import ILU0
+    case = cases.rijke3d()
+    mats = gpu_operators(case)
+    csr = (mats.A + (400 * np.pi) ** 2 * mats.C).csr()
+    ilu = ILU0(be(), csr)
+    rng = np.random.default_rng(2)
+    bvec = rng.standard_normal(csr.n_rows) + 1j * rng.standard_normal(csr.n_rows)
+    x = be().zeros(csr.n_rows)
+    ilu.solve(be().asarray(bvec, dtype=torch.complex128), x)
+    # host ILU(0) on the same pattern
+    ip, ix, v = csr.indptr.cpu().numpy(), csr.indices.cpu().numpy(), csr.values.cpu().numpy().copy()
+    n = csr.n_rows
+    diag = np.array([ip[i] + np.searchsorted(ix[ip[i]:ip[i + 1]], i) for i in range(n)])
+    for i in range(n):
+        for kk in range(ip[i], diag[i]):
+            k = ix[kk]
+            v[kk] /= v[diag[k]]
+            cols_k = ix[diag[k] + 1:ip[k + 1]]
+            pos = ip[i] + np.searchsorted(ix[ip[i]:ip[i + 1]], cols_k)
+            ok = (pos < ip[i + 1]) & (ix[np.minimum(pos, ip[i + 1] - 1)] == cols_k)
+            v[pos[ok]] -= v[kk] * v[diag[k] + 1:ip[k + 1]][ok]
+    xs = bvec.copy()
+    for i in range(n):
+        xs[i] -= v[ip[i]:diag[i]] @ xs[ix[ip[i]:diag[i]]]
+    for i in range(n - 1, -1, -1):
+        xs[i] = (xs[i] - v[diag[i] + 1:ip[i + 1]] @ xs[ix[diag[i] + 1:ip[i + 1]]]) / v[diag[i]]
+    assert relmax(x.cpu().numpy(), xs) < 1e-10
+
+
+# ---------------------------------------------------------------------------- K9 + a7-a10
+def test_amg_vcycle_matches_host_double_and_gmres_converges():
+    from helmholtz_x_b200.operators import ShiftedSolver
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    s = case.target
+    solver = ShiftedSolver(mats.ops, {"A": 1.0, "B": s, "C": s ** 2}, rtol=1e-11)
+    rng = np.random.default_rng(4)
+    n = mats.ops.n
+    bvec = be().asarray(rng.standard_normal(n) + 1j * rng.standard_normal(n), dtype=torch.complex128)
+    x = be().zeros(n)
+    solver.solve(bvec, x)
+    P = solver.P.to_scipy()
+    res = np.linalg.norm(P @ x.cpu().numpy() - bvec.cpu().numpy()) / np.linalg.norm(bvec.cpu().numpy())
+    assert res < 1e-10
+    assert mats.ops.stats["inner_iterations"] <= 60, mats.ops.stats
+
+
+def test_passive_eps_matches_golden():
+    """.../RijkeTube3D/Results/Passive/passive.log:30-33"""
+    from helmholtz_x_b200.eigensolvers import eps_solver
+    case = cases.rijke3d()
+    mats = gpu_operators(case, passive=True)
+    E = eps_solver(mats.A, mats.C, case.target, nev=2)
+    lam = np.array([E.getEigenvalue(i) for i in range(2)])
+    gold = G["rijke3d_passive_eps"]["lambdas"][0]
+    assert min(abs(lam - gold)) / gold < EIG_RTOL
+
+
+def _run_fpi(case, problem_type="direct", **kw):
+    from helmholtz_x_b200.eigensolvers import fixed_point_iteration
+    mats = gpu_operators(case)
+    D = gpu_flame(case)
+    D.assemble_submatrices(problem_type)
+    target = case.target if problem_type == "direct" else np.conj(case.target)
+    E = fixed_point_iteration(mats, D, target, nev=case.nev, i=0, tol=case.tol, problem_type=problem_type, **kw)
+    return mats, D, E
+
+
+def _check_history(hist, gold, rtol=EIG_RTOL, atol=0.0):
+    assert len(hist) >= len(gold)
+    for a, b in zip(hist[-len(gold):], gold):
+        assert abs(a - b) <= rtol * abs(b) + atol, (a, b)
+
+
+def test_fpi_rijke3d_config1_matches_golden_log_and_eigenvector():
+    """config 1: .../RijkeTube3D/Results/Active/active.log:23-52 and Results/Active/p.h5"""
+    from helmholtz_x_b200.eigenvectors import normalize_eigenvector
+    from scipy.spatial import cKDTree
+    case = cases.rijke3d()
+    mats, D, E = _run_fpi(case)
+    gold = [cases.cplx(p) for p in G["rijke3d_active_fpi"]["omegas"]]
+    _check_history(E.omega_history, gold, atol=6e-9)       # log prints 8 decimals
+    omega, p = normalize_eigenvector(mats.mesh, E, 0, degree=1, which='right', matrices=mats)
+    gp = np.load(cases.GOLDEN_DIR + "/rijke3d_active_p.npz")
+    _, idx = cKDTree(case.mesh.x).query(gp["geometry"])
+    pm, pg = p.x.array[idx], gp["p"]
+    sgn = 1 if abs(pm[0] - pg[0]) < abs(pm[0] + pg[0]) else -1
+    assert np.abs(sgn * pm - pg).max() / np.abs(pg).max() < 1e-7
+
+
+def test_fpi_prf_pep_direct_and_adjoint_match_golden():
+    case = cases.prf_rijke3d()
+    _, _, E = _run_fpi(case)
+    _check_history(E.omega_history, [cases.cplx(p) for p in G["prf_rijke3d_direct_fpi"]["omegas"]], atol=6e-9)
+    _, _, E2 = _run_fpi(case, "adjoint")
+    _check_history(E2.omega_history, [cases.cplx(p) for p in G["prf_rijke3d_adjoint_fpi"]["omegas"]], atol=6e-9)
+
+
+def test_fpi_rijkeffd_config5_eigenpair_matches_golden():
+    """.../RijkeFFD/Results/Original/eigenvalues.txt"""
+    case = cases.rijkeffd()
+    _, _, E = _run_fpi(case)
+    g = cases.cplx(G["rijkeffd_eigenvalues"]["direct"])
+    assert abs(E.getEigenpair(0) - g) / abs(g) < EIG_RTOL
+    _, _, E2 = _run_fpi(case, "adjoint")
+    g = cases.cplx(G["rijkeffd_eigenvalues"]["adjoint"])
+    assert abs(E2.getEigenpair(0) - g) / abs(g) < EIG_RTOL
+
+
+def test_fpi_annulus_config3_matches_golden():
+    """.../fullAnnulus/Results/Active/FPI/active.log:43-92 and eigenvalues_dir.txt"""
+    case = cases.annulus()
+    _, _, E = _run_fpi(case)
+    gold = [cases.cplx(p) for p in G["annulus_fpi_direct"]["omegas"]]
+    _check_history(E.omega_history, gold, rtol=0, atol=6e-4)        # log prints 3 decimals
+    g1 = cases.cplx(G["annulus_fpi_eigenvalues_dir"]["direct_1"])
+    g2 = cases.cplx(G["annulus_fpi_eigenvalues_dir"]["direct_2"])
+    assert abs(E.getEigenpair(0) - g1) / abs(g1) < EIG_RTOL
+    assert abs(E.getEigenpair(1) - g2) / abs(g2) < EIG_RTOL
+
+
+def test_newton_annulus_config3_matches_golden():
+    """.../fullAnnulus/Results/Active/NewtonSolver/{active.log:41-149,eigenvalues.txt}, i=0"""
+    from helmholtz_x_b200.eigensolvers import newtonSolver
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    D = gpu_flame(case)
+    D.assemble_submatrices('direct')
+    omega, p = newtonSolver(mats, D, case.newton_init, i=0, nev=case.newton_nev, tol=case.newton_tol)
+    g = cases.cplx(G["annulus_newton_eigenvalues"]["direct_1"])
+    assert abs(omega - g) / abs(g) < EIG_RTOL
+
+
+def test_p2_fpi_matches_oracle():
+    """P2 has no usable reference golden ('parity unpinned'); the oracle is the target."""
+    case = degree_case("prf", 2)
+    _, _, E = _run_fpi(case)
+    ops = cases.oracle_operators(case)
+    fl = cases.oracle_flame(case)
+    Eo, hist = ox.fixed_point_iteration(ops, fl, case.target, nev=case.nev, i=0, tol=case.tol)
+    assert abs(E.getEigenpair(0) - Eo.omega(0)) / abs(Eo.omega(0)) < EIG_RTOL
+
+
+# ---------------------------------------------------------------------------- size-independent properties
+def test_large_synthetic_annulus_properties():
+    """Full-size properties where the oracle is too slow: linearity of the SpMV, A 1 = 0
+    (constants are in the kernel of the stiffness form), sum(C) = domain volume."""
+    from helmholtz_x_b200 import fem, synthetic
+    g = synthetic.annulus_grid(24, 384, 96, device="cuda")
+    mesh = fem.Mesh(g["x"], g["cells"], g["cell_tags"], g["facets"], g["facet_tags"])
+    V = fem.functionspace(mesh, ("Lagrange", 1))
+    c = synthetic.annulus_sound_speed(mesh.x, mesh.cells)
+    a, cv = fem.assemble_AC(V, c)
+    A, C = V.matrix(a), V.matrix(cv)
+    b = be()
+    one = b.zeros(V.n) + 1.0
+    y = b.zeros(V.n)
+    b.spmv(A, one, y)
+    assert float(y.abs().max()) < 1e-6 * float(a.abs().max())
+    b.spmv(C, one, y)
+    vol = float(mesh.volumes().sum())
+    assert abs(float(y.real.sum()) - vol) < 1e-12 * vol * V.n ** 0.5
+    x1 = torch.randn(V.n, dtype=torch.float64, device=b.device).to(torch.complex128)
+    x2 = torch.randn(V.n, dtype=torch.float64, device=b.device).to(torch.complex128) * 1j
+    y1, y2, y3 = b.zeros(V.n), b.zeros(V.n), b.zeros(V.n)
+    b.spmv(A, x1, y1); b.spmv(A, x2, y2); b.spmv(A, x1 + 2 * x2, y3)
+    assert float((y3 - y1 - 2 * y2).abs().max()) < 1e-12 * float(y3.abs().max())
