@@ -278,6 +278,7 @@ using namespace hx;
 extern "C" int hx_spmv_zz(int n, const int32_t* indptr, const int32_t* indices, const double* vals,
                           const double* x, double* y, const double* alpha_h, const double* beta_h,
                           const double* y0, int lanes, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
     if (!indptr || !indices || !vals || !x || !y) return fail(HX_ERR_ARG, "hx_spmv_zz: null pointer%s%s");
     double2 alpha = alpha_h ? h2c(alpha_h) : make_double2(1.0, 0.0);
     double2 beta = beta_h ? h2c(beta_h) : make_double2(1.0, 0.0);
@@ -289,6 +290,7 @@ extern "C" int hx_spmv_zz(int n, const int32_t* indptr, const int32_t* indices, 
 extern "C" int hx_spmv_dz(int n, const int32_t* indptr, const int32_t* indices, const double* vals,
                           const double* x, double* y, const double* alpha_h, const double* beta_h,
                           const double* y0, int lanes, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
     if (!indptr || !indices || !vals || !x || !y) return fail(HX_ERR_ARG, "hx_spmv_dz: null pointer%s%s");
     double2 alpha = alpha_h ? h2c(alpha_h) : make_double2(1.0, 0.0);
     double2 beta = beta_h ? h2c(beta_h) : make_double2(1.0, 0.0);

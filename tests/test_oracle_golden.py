@@ -1,0 +1,129 @@
+"""Pin the CPU oracle against the reference's committed golden logs / eigenvalue files /
+eigenvector .h5 files.  These are the known-answer tests the
+reference itself ships (it has no unit tests)."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from oracle import hx_oracle as ox
+from tests import cases
+
+G = cases.golden_values()
+
+
+def _hist_close(hist, gold, atol):
+    assert len(hist) >= len(gold)
+    for a, b in zip(hist[-len(gold):], gold):
+        assert abs(a - b) < atol, (a, b)
+
+
+def test_rijke3d_config1_fpi_log_and_eigenvector():
+    """.../RijkeTube3D/Results/Active/active.log:23-52, Results/Active/p.h5 (2426 complex nodal values)"""
+    case = cases.rijke3d()
+    ops = cases.oracle_operators(case)
+    assert ops.A.shape == (2426, 2426) and ops.A.nnz == 27980 and ops.B is None
+    fl = cases.oracle_flame(case)
+    assert (np.count_nonzero(fl.left), np.count_nonzero(fl.right)) == (558, 569)
+    assert fl.dense_block_nnz() == 317502                       # the block the reference densifies
+    E, hist = ox.fixed_point_iteration(ops, fl, case.target, nev=2, i=0, tol=1e-8)
+    _hist_close(hist, [cases.cplx(p) for p in G["rijke3d_active_fpi"]["omegas"]], 1e-8)
+    _, p = ox.normalize_eigenvector(ops, E, 0)
+    gp = np.load(os.path.join(cases.GOLDEN_DIR, "rijke3d_active_p.npz"))
+    d, idx = cKDTree(case.mesh.x).query(gp["geometry"])
+    assert d.max() < 1e-12
+    pm, pg = p[idx], gp["p"]
+    s = 1 if abs(pm[0] - pg[0]) < abs(pm[0] + pg[0]) else -1
+    assert np.abs(s * pm - pg).max() / np.abs(pg).max() < 1e-12
+
+
+def test_rijke3d_passive_eps():
+    """.../RijkeTube3D/Results/Passive/passive.log:30-33"""
+    case = cases.rijke3d()
+    ops = cases.oracle_operators(case, passive=True)
+    E = ox.eps_solve(ops.A, -ops.C, case.target ** 2, 4)
+    lam = np.sort(E.eigenvalues.real)
+    gold = np.sort(G["rijke3d_passive_eps"]["lambdas"])
+    assert abs(lam[0]) < 1e-4
+    assert np.allclose(lam[1:], gold[1:], rtol=1e-10)
+
+
+def test_prf_rijke3d_robin_pep_direct_and_adjoint():
+    """.../PRF/RijkeTube3D/Results/Active/active.log:21-50,57-86"""
+    case = cases.prf_rijke3d()
+    ops, fl = cases.oracle_operators(case), cases.oracle_flame(case)
+    _, h = ox.fixed_point_iteration(ops, fl, case.target, nev=2, i=0)
+    _hist_close(h, [cases.cplx(p) for p in G["prf_rijke3d_direct_fpi"]["omegas"]], 1e-8)
+    _, h = ox.fixed_point_iteration(ops, fl, case.target, nev=2, i=0, problem_type="adjoint")
+    _hist_close(h, [cases.cplx(p) for p in G["prf_rijke3d_adjoint_fpi"]["omegas"]], 1e-8)
+
+
+def test_rijkeffd_config5_eigenpair():
+    """.../RijkeFFD/Results/Original/{results.log:21-57,eigenvalues.txt}"""
+    case = cases.rijkeffd()
+    ops, fl = cases.oracle_operators(case), cases.oracle_flame(case)
+    E, h = ox.fixed_point_iteration(ops, fl, case.target, nev=2, i=0)
+    _hist_close(h, [cases.cplx(p) for p in G["rijkeffd_direct_fpi"]["omegas"]], 1e-8)
+    g = cases.cplx(G["rijkeffd_eigenvalues"]["direct"])
+    assert abs(E.omega(0) - g) / abs(g) < 1e-11
+
+
+def test_annulus_config3_first_iterate():
+    """.../fullAnnulus/Results/Active/FPI/active.log:43-50 (first fixed-point iterate; the
+    whole run is recorded in tests/golden/oracle_recorded.json)"""
+    case = cases.annulus()
+    ops, fl = cases.oracle_operators(case), cases.oracle_flame(case)
+    assert ops.A.shape[0] == 34787 and ops.A.nnz == 464207
+    E0 = ox.pep_solve(ops.A, ops.B, ops.C, case.target, case.nev)
+    U, W = ox._flame_UW(fl, E0.eigenvalues[0], "direct")
+    E1 = ox.pep_solve(ops.A, ops.B, ops.C, case.target, case.nev, U, W)
+    om1 = 0.5 * E1.eigenvalues[0] + 0.5 * E0.eigenvalues[0]
+    assert abs(om1 - cases.cplx(G["annulus_fpi_direct"]["omegas"][0])) < 6e-4
+
+
+def test_recorded_full_annulus_runs_match_goldens():
+    with open(os.path.join(cases.GOLDEN_DIR, "oracle_recorded.json")) as fh:
+        rec = json.load(fh)
+    for key, gkey, gname in (("annulus_fpi_direct_1", "annulus_fpi_eigenvalues_dir", "direct_1"),
+                             ("annulus_fpi_direct_2", "annulus_fpi_eigenvalues_dir", "direct_2"),
+                             ("annulus_newton_direct_1", "annulus_newton_eigenvalues", "direct_1")):
+        a, b = cases.cplx(rec[key]), cases.cplx(G[gkey][gname])
+        assert abs(a - b) / abs(b) < 1e-12
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(not os.environ.get("HX_SLOW"), reason="long oracle run; set HX_SLOW=1")
+def test_annulus_full_fpi_and_newton_slow():
+    case = cases.annulus()
+    ops, fl = cases.oracle_operators(case), cases.oracle_flame(case)
+    E, h = ox.fixed_point_iteration(ops, fl, case.target, nev=case.nev, i=0, tol=case.tol)
+    g = cases.cplx(G["annulus_fpi_eigenvalues_dir"]["direct_1"])
+    assert abs(E.omega(0) - g) / abs(g) < 1e-11
+    om, _, _ = ox.newton_solver(ops, fl, case.newton_init, nev=2, i=0, tol=case.newton_tol)
+    g = cases.cplx(G["annulus_newton_eigenvalues"]["direct_1"])
+    assert abs(om - g) / abs(g) < 1e-11
+
+
+def test_ftf_matches_reference_formulas():
+    """flame_transfer_function.py:10-14,25-42"""
+    f = ox.NTau(0.1, 0.0015)
+    om = 1200 + 5j
+    assert abs(f(om) - 0.1 * np.exp(1j * om * 0.0015)) < 1e-15
+    d = (f(om + 1e-6) - f(om - 1e-6)) / 2e-6
+    assert abs(f.derivative(om) - d) < 1e-8
+    ss = cases.make_ftf(cases.annulus().ftf)
+    d = (ss(om + 1e-2) - ss(om - 1e-2)) / 2e-2
+    assert abs(ss.derivative(om) - d) < 1e-8 * abs(d)
+
+
+def test_p2_space_and_operators_are_consistent():
+    """P2 is 'parity unpinned' by the reference; check internal consistency of the oracle."""
+    case = cases.rijke3d()
+    case["degree"] = 2
+    ops = cases.oracle_operators(case)
+    one = np.ones(ops.A.shape[0])
+    assert np.abs(ops.A @ one).max() < 1e-6 * np.abs(ops.A.data).max()
+    vol, _ = ox.geometry(case.mesh)
+    assert abs(one @ (ops.C @ one) - vol.sum()) < 1e-12
