@@ -137,23 +137,24 @@ def gpu_step(g, degree, mesh=None, return_objects=False):
     return omega, p
 
 
-def spmv_roofline(be, csr, launches=200, warmup=50):
-    """Average duration of hx_spmv_zz on this matrix (CUDA events on the launching stream)."""
+def spmv_roofline(be, M, launches=200, warmup=50):
+    """Average duration of the complex128 SpMV on this matrix (CSR or SELL-32), CUDA
+    events on the launching stream.  Bytes: the CSR model 20*nnz + 36*n."""
     import torch
-    x = torch.randn(csr.n_cols, dtype=torch.float64, device=be.device, generator=torch.Generator(be.device).manual_seed(0)).to(torch.complex128)
-    y = be.zeros(csr.n_rows)
+    x = torch.randn(M.n_cols, dtype=torch.float64, device=be.device, generator=torch.Generator(be.device).manual_seed(0)).to(torch.complex128)
+    y = be.zeros(M.n_rows)
     for _ in range(warmup):
-        be.spmv(csr, x, y)
+        be.spmv(M, x, y)
     st = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(st)
     for _ in range(launches):
-        be.spmv(csr, x, y)
+        be.spmv(M, x, y)
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / launches
-    nbytes = 20.0 * csr.nnz + 36.0 * csr.n_rows
+    nbytes = 20.0 * M.nnz + 36.0 * M.n_rows
     return ms, nbytes
 
 
@@ -224,17 +225,21 @@ def run_b200(args):
         step_s, e2e_s = float(t[0]), float(t[1])
     # ---- SpMV roofline on the workload's P(sigma) ------------------------------------------------
     peak, peak_src = measured_peak()
+    from helmholtz_x_b200.sell import SellMatrix
     csr = (mats.A + TARGET * mats.B + TARGET ** 2 * mats.C).csr()
-    ms, nbytes = spmv_roofline(be, csr)
+    sell = SellMatrix.from_csr(be, csr)
+    ms, nbytes = spmv_roofline(be, sell)
+    ms_csr, _ = spmv_roofline(be, csr)
     achieved = nbytes / (ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "spmv_csr_kernel<8,double2> (hx_spmv_zz)", "achieved": round(achieved, 1),
-            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-            "bytes_per_launch": nbytes, "ms_per_launch": round(ms, 5), "n": csr.n_rows, "nnz": csr.nnz,
-            "model": "20*nnz + 36*n bytes (SURVEY 8d)"}
+    roof = {"bound": "hbm", "kernel": "sell_kernel<4,6,0> (hx_spmv_sell_zz, the solver's fine-level SpMV format)",
+            "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None, "bytes_per_launch": nbytes,
+            "ms_per_launch": round(ms, 5), "n": csr.n_rows, "nnz": csr.nnz, "model": "20*nnz + 36*n bytes (SURVEY 8d)",
+            "csr_vector_gbs": round(nbytes / (ms_csr * 1e-3) / 1e9, 1)}
     big = None
     if args.spmv_dofs and rank == 0:
         try:
-            del mats, E, csr
+            del mats, E, csr, sell
             torch.cuda.empty_cache()
             from helmholtz_x_b200 import synthetic
             gb = workload(args.spmv_dofs, 1)
@@ -248,23 +253,12 @@ def run_b200(args):
             gbs = nbb / (msb * 1e-3) / 1e9
             big = {"n": cb.n_rows, "nnz": cb.nnz, "ms_per_launch": round(msb, 4), "gbs": round(gbs, 1),
                    "frac_of_measured_peak": round(gbs / peak, 4), "frac_of_8TBs_nominal": round(gbs / 8000.0, 4)}
-            try:
-                from helmholtz_x_b200.sell import SellMatrix
-                sm = SellMatrix.from_csr(be, cb)
-                x = torch.randn(cb.n_cols, dtype=torch.float64, device=be.device).to(torch.complex128)
-                y = be.zeros(cb.n_rows)
-                for _ in range(10):
-                    sm.spmv(x, y)
-                e0.record(st)
-                for _ in range(50):
-                    sm.spmv(x, y)
-                e1.record(st)
-                torch.cuda.synchronize()
-                mss = e0.elapsed_time(e1) / 50
-                big["sell32_gbs"] = round(nbb / (mss * 1e-3) / 1e9, 1)
-                big["sell32_padding"] = round(sm.padding_ratio, 4)
-            except Exception as ex:          # noqa: BLE001
-                big["sell32_error"] = str(ex)[:200]
+            sm = SellMatrix.from_csr(be, cb)
+            mss, _ = spmv_roofline(be, sm, launches=100, warmup=20)
+            big["sell32_gbs"] = round(nbb / (mss * 1e-3) / 1e9, 1)
+            big["sell32_frac_of_measured_peak"] = round(big["sell32_gbs"] / peak, 4)
+            big["sell32_frac_of_8TBs_nominal"] = round(big["sell32_gbs"] / 8000.0, 4)
+            big["sell32_padding"] = round(sm.padding_ratio, 4)
         except Exception as ex:              # noqa: BLE001
             big = {"error": str(ex)[:300]}
     out = {

@@ -30,9 +30,11 @@ SIGNATURES = {
     "hx_launch_count_reset": [],
     "hx_spmv_zz": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "hx_spmv_dz": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
-    "hx_spmv_sell_zz": [i32, i32, vp, vp, vp, vp, vp, vp, vp],
+    "hx_spmv_sell_zz": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "hx_jacobi_sell": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp],
     "hx_sell_slice_widths": [i32, vp, vp, i32, vp, vp],
-    "hx_sell_fill": [i32, vp, vp, vp, vp, i32, vp, vp, vp, vp],
+    "hx_sell_fill": [i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
+    "hx_sell_gather": [i64, vp, vp, vp, vp],
     "hx_combine_abc": [i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_lowrank_dots": [i32, vp, vp, vp, vp, vp, vp],
     "hx_lowrank_update": [i32, vp, vp, vp, vp, vp, vp, vp, vp],

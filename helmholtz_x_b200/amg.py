@@ -91,9 +91,10 @@ class Level:
 
 class AMG:
     def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=8,
-                 coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0):
+                 coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=20000):
         """A, C real-valued, B complex or None -- all on ONE shared fine pattern."""
         self.be, self.nu, self.omega = be, nu, omega
+        self.sell_min_rows = sell_min_rows if getattr(be, "supports_sell", False) else None
         dev = A.values.device
         self.levels = []
         a_re = A.values
@@ -164,6 +165,8 @@ class AMG:
         for L in self.levels:
             L.x = be.zeros(L.n); L.b_ = be.zeros(L.n); L.r = be.zeros(L.n); L.t = be.zeros(L.n)
             L.M = None
+            L.Mop = None
+            L.sellp = None
             L.dinv = be.zeros(L.n)
         self.coarse_inv = None
 
@@ -185,8 +188,15 @@ class AMG:
                 vals = be.empty(L.pattern.nnz)
                 be.combine_abc(L.a, L.b, L.c, ca, cb, cc, vals)
             L.M = L.pattern.with_values(vals)
+            L.Mop = L.M
             if i < len(self.levels) - 1:
                 be.diag_inv(L.M, L.dinv)
+                if self.sell_min_rows is not None and L.n >= self.sell_min_rows:
+                    from .sell import SellMatrix, SellPattern
+                    if L.sellp is None:
+                        L.sellp = SellPattern(be, L.pattern.indptr, L.pattern.indices, L.n, L.n)
+                        L.sell_vals = be.empty(max(L.sellp.total, 1))
+                    L.Mop = SellMatrix(L.sellp, L.sellp.values_from_csr(vals, out=L.sell_vals))
         L = self.levels[-1]
         dense = torch.zeros(L.n, L.n, dtype=c128, device=L.M.values.device)
         rows = _rows_of(L.M.indptr, L.M.nnz)
@@ -200,16 +210,20 @@ class AMG:
     def fine_matrix(self):
         return self.levels[0].M
 
+    def fine_operator(self):
+        """The fine-level operator in its fastest SpMV format (SELL-32 when large)."""
+        return self.levels[0].Mop
+
     def _smooth(self, L, b, x, first_zero):
         """nu damped-Jacobi sweeps; result ends in L.x.  x is L.x."""
         be = self.be
         cur, other = L.x, L.t
         n_sweeps = self.nu
         if first_zero:
-            be.jacobi_sweep(L.M, L.dinv, b, None, cur, self.omega)
+            be.jacobi_sweep(L.Mop, L.dinv, b, None, cur, self.omega)
             n_sweeps -= 1
         for _ in range(n_sweeps):
-            be.jacobi_sweep(L.M, L.dinv, b, cur, other, self.omega)
+            be.jacobi_sweep(L.Mop, L.dinv, b, cur, other, self.omega)
             cur, other = other, cur
         if cur is not L.x:
             L.x, L.t = cur, other      # swap the roles of the buffers
@@ -222,7 +236,7 @@ class AMG:
             be.dense_gemv(self.coarse_inv, b, L.x)
             return L.x
         self._smooth(L, b, L.x, first_zero=True)
-        be.spmv(L.M, L.x, L.r, alpha=-1.0, beta=1.0, y0=b)           # r = b - M x
+        be.spmv(L.Mop, L.x, L.r, alpha=-1.0, beta=1.0, y0=b)         # r = b - M x
         Lc = self.levels[i + 1]
         be.spmv(L.R, L.r, Lc.b_)
         xc = self._cycle(i + 1, Lc.b_)

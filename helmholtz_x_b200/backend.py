@@ -23,12 +23,14 @@ def _c2(z):
 
 
 def choose_lanes(nnz, n_rows):
+    """Threads per row of the CSR-vector kernel (measured on B200, 10M-DoF annulus:
+    14.8 nnz/row -> 4 lanes 4.6 TB/s, 8 lanes 4.0 TB/s; profiles/r1_spmv_bench_10m_v1.json)."""
     mean = nnz / max(n_rows, 1)
-    if mean <= 6:
+    if mean <= 18:
         return 4
-    if mean <= 20:
+    if mean <= 40:
         return 8
-    if mean <= 48:
+    if mean <= 96:
         return 16
     return 32
 
@@ -82,6 +84,7 @@ class LowRank:
 
 class CudaBackend:
     name = "cuda"
+    supports_sell = True
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():
@@ -117,6 +120,8 @@ class CudaBackend:
     # ---- sparse -----------------------------------------------------------------
     def spmv(self, M: CsrMatrix, x, y, alpha=1.0, beta=None, y0=None, lanes=None):
         """y = alpha*M@x (+ beta*y0)."""
+        if getattr(M, "is_sell", False):
+            return M.spmv(x, y, alpha=None if (alpha == 1.0 and beta is None) else alpha, beta=beta, y0=y0)
         assert x.dtype == c128 and y.dtype == c128 and x.is_contiguous() and y.is_contiguous()
         assert x.numel() >= M.n_cols and y.numel() >= M.n_rows
         name = "hx_spmv_zz" if M.values.dtype == c128 else "hx_spmv_dz"
@@ -189,10 +194,16 @@ class CudaBackend:
                   out.data_ptr(), self.stream)
         return out
 
-    def jacobi_sweep(self, M: CsrMatrix, dinv, b, xin, xout, omega):
-        _lib.call("hx_jacobi_sweep", M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(),
-                  dinv.data_ptr(), b.data_ptr(), xin.data_ptr() if xin is not None else None, xout.data_ptr(),
-                  float(omega), M.lanes, self.stream)
+    def jacobi_sweep(self, M, dinv, b, xin, xout, omega):
+        """xout = xin + omega*dinv*(b - M xin); xin None => xout = omega*dinv*b (matrix unused)."""
+        if xin is None:
+            _lib.call("hx_jacobi_sweep", M.n_rows, None, None, None, dinv.data_ptr(), b.data_ptr(), None, xout.data_ptr(),
+                      float(omega), 8, self.stream)
+        elif getattr(M, "is_sell", False):
+            M.jacobi(dinv, b, xin, xout, omega)
+        else:
+            _lib.call("hx_jacobi_sweep", M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(),
+                      dinv.data_ptr(), b.data_ptr(), xin.data_ptr(), xout.data_ptr(), float(omega), M.lanes, self.stream)
         return xout
 
     def dense_inverse(self, A):

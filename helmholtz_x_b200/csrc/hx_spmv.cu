@@ -127,10 +127,13 @@ __global__ void diag_pos_kernel(int n, const int* __restrict__ indptr, const int
 }
 
 // ---- SELL-32: one thread per row, column-major inside a 32-row slice ----------
-__global__ void __launch_bounds__(256)
-spmv_sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, const int* __restrict__ cols,
-                 const double2* __restrict__ vals, const int* __restrict__ row_perm,
-                 const double2* __restrict__ x, double2* __restrict__ y) {
+// MODE 0: y = acc; 1: y = alpha*acc + beta*y0; 2: Jacobi xout = xin + omega*dinv*(b - acc)
+template <int UNROLL, int MINB, int MODE>
+__global__ void __launch_bounds__(256, MINB)
+sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, const int* __restrict__ cols,
+            const double2* __restrict__ vals, const int* __restrict__ row_perm, const double2* __restrict__ x,
+            double2* __restrict__ y, double2 alpha, double2 beta, const double2* __restrict__ y0,
+            const double2* __restrict__ dinv, const double2* __restrict__ b, double omega) {
     const int slice = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (slice >= n_slices) return;
@@ -138,25 +141,39 @@ spmv_sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, c
     const int width = (int)((slice_ptr[slice + 1] - base) >> 5);
     const int* c = cols + base + lane;
     const double2* v = vals + base + lane;
-    double2 a0 = make_double2(0, 0), a1 = a0, a2 = a0, a3 = a0;
+    double2 acc[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc[u] = make_double2(0.0, 0.0);
     int j = 0;
-    for (; j + 4 <= width; j += 4) {
-        const int c0 = ld_stream(c + 32 * j), c1 = ld_stream(c + 32 * (j + 1));
-        const int c2 = ld_stream(c + 32 * (j + 2)), c3 = ld_stream(c + 32 * (j + 3));
-        const double2 v0 = ld_stream(v + 32 * j), v1 = ld_stream(v + 32 * (j + 1));
-        const double2 v2 = ld_stream(v + 32 * (j + 2)), v3 = ld_stream(v + 32 * (j + 3));
-        cfma(a0, v0, __ldg(x + c0));
-        cfma(a1, v1, __ldg(x + c1));
-        cfma(a2, v2, __ldg(x + c2));
-        cfma(a3, v3, __ldg(x + c3));
+    for (; j + UNROLL <= width; j += UNROLL) {
+        int cc[UNROLL];
+        double2 vv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) cc[u] = ld_stream(c + 32 * (j + u));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) vv[u] = ld_stream(v + 32 * (j + u));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) cfma(acc[u], vv[u], __ldg(x + cc[u]));
     }
     for (; j < width; ++j) {
         const int c0 = ld_stream(c + 32 * j);
         const double2 v0 = ld_stream(v + 32 * j);
-        cfma(a0, v0, __ldg(x + c0));
+        cfma(acc[0], v0, __ldg(x + c0));
     }
+#pragma unroll
+    for (int u = 1; u < UNROLL; ++u) acc[0] = cadd(acc[0], acc[u]);
     const int r = slice * 32 + lane;
-    if (r < n) y[row_perm[r]] = cadd(cadd(a0, a1), cadd(a2, a3));
+    if (r >= n) return;
+    const int row = row_perm[r];
+    if (MODE == 0) y[row] = acc[0];
+    else if (MODE == 1) {
+        double2 res = cmul(alpha, acc[0]);
+        if (y0) res = cadd(res, cmul(beta, y0[row]));
+        y[row] = res;
+    } else {
+        const double2 res = csub(b[row], acc[0]);
+        y[row] = cadd(x[row], cscale(omega, cmul(dinv[row], res)));
+    }
 }
 
 __global__ void sell_widths_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ row_perm,
@@ -175,7 +192,7 @@ __global__ void sell_widths_kernel(int n, const int* __restrict__ indptr, const 
 __global__ void sell_fill_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
                                  const double2* __restrict__ vals, const int* __restrict__ row_perm, int n_slices,
                                  const long long* __restrict__ slice_ptr, int* __restrict__ cols,
-                                 double2* __restrict__ svals) {
+                                 double2* __restrict__ svals, int* __restrict__ src) {
     const int slice = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (slice >= n_slices) return;
@@ -186,8 +203,25 @@ __global__ void sell_fill_kernel(int n, const int* __restrict__ indptr, const in
     if (r < n) { row = row_perm[r]; start = indptr[row]; len = indptr[row + 1] - start; }
     for (int j = 0; j < width; ++j) {
         const long long p = base + 32LL * j + lane;
-        if (j < len) { cols[p] = indices[start + j]; svals[p] = vals[start + j]; }
-        else { cols[p] = row; svals[p] = make_double2(0.0, 0.0); }   // padding: harmless gather of own row
+        if (j < len) {
+            cols[p] = indices[start + j];
+            if (svals) svals[p] = vals[start + j];
+            if (src) src[p] = start + j;
+        } else {                                  // padding: harmless gather of own row, value 0
+            cols[p] = row;
+            if (svals) svals[p] = make_double2(0.0, 0.0);
+            if (src) src[p] = -1;
+        }
+    }
+}
+
+__global__ void sell_gather_kernel(long long total, const int* __restrict__ src, const double2* __restrict__ csr_vals,
+                                   double2* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int s = ld_stream(src + i);
+        out[i] = (s >= 0) ? csr_vals[s] : make_double2(0.0, 0.0);
     }
 }
 
@@ -237,16 +271,6 @@ __global__ void lowrank_update_kernel(int nrows, const int* __restrict__ lrow, c
     for (int k = lptr[i]; k < lptr[i + 1]; ++k) rfma(acc, lval[k], t[lcol[k]]);
     const int row = lrow[i];
     y[row] = cadd(y[row], cmul(coef, acc));
-}
-
-static int pick_lanes(int n, const int* indptr_dev_unused, long long nnz_hint, int lanes) {
-    if (lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
-    (void)indptr_dev_unused;
-    double mean = n > 0 ? (double)nnz_hint / n : 0.0;
-    if (mean <= 6) return 4;
-    if (mean <= 20) return 8;
-    if (mean <= 48) return 16;
-    return 32;
 }
 
 template <typename VT>
@@ -299,14 +323,49 @@ extern "C" int hx_spmv_dz(int n, const int32_t* indptr, const int32_t* indices, 
                                (const double2*)y0, lanes, (cudaStream_t)stream);
 }
 
-extern "C" int hx_spmv_sell_zz(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols,
-                               const double* vals, const int32_t* row_perm, const double* x, double* y,
-                               hx_stream_t stream) {
-    if (n <= 0) return HX_OK;
+namespace hx {
+template <int MODE>
+static int launch_sell(int variant, int n, int n_slices, const long long* sp, const int* cols, const double2* vals,
+                       const int* perm, const double2* x, double2* y, double2 alpha, double2 beta, const double2* y0,
+                       const double2* dinv, const double2* b, double omega, cudaStream_t st) {
     const int warps = 8;
-    spmv_sell_kernel<<<ceil_div(n_slices, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-        n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm, (const double2*)x, (double2*)y);
-    return check_launch("spmv_sell_kernel");
+    const int grid = ceil_div(n_slices, warps);
+#define HX_SELL(U, MB)                                                                                          \
+    sell_kernel<U, MB, MODE><<<grid, warps * 32, 0, st>>>(n, n_slices, sp, cols, vals, perm, x, y, alpha, beta, y0, dinv, b, omega)
+    switch (variant) {
+        case 1: HX_SELL(4, 4); break;
+        case 2: HX_SELL(4, 6); break;
+        case 3: HX_SELL(2, 8); break;
+        case 4: HX_SELL(4, 8); break;
+        case 5: HX_SELL(8, 4); break;
+        case 0: default: HX_SELL(4, 6); break;
+    }
+#undef HX_SELL
+    return check_launch("sell_kernel");
+}
+}  // namespace hx
+
+extern "C" int hx_spmv_sell_zz(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols, const double* vals,
+                               const int32_t* row_perm, const double* x, double* y, const double* alpha_h,
+                               const double* beta_h, const double* y0, int variant, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    const double2 one = make_double2(1.0, 0.0);
+    if (!alpha_h && !y0)
+        return launch_sell<0>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
+                              (const double2*)x, (double2*)y, one, one, nullptr, nullptr, nullptr, 0.0, (cudaStream_t)stream);
+    return launch_sell<1>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
+                          (const double2*)x, (double2*)y, alpha_h ? h2c(alpha_h) : one, beta_h ? h2c(beta_h) : one,
+                          (const double2*)y0, nullptr, nullptr, 0.0, (cudaStream_t)stream);
+}
+
+extern "C" int hx_jacobi_sell(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols, const double* vals,
+                              const int32_t* row_perm, const double* dinv, const double* b, const double* xin,
+                              double* xout, double omega, int variant, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    const double2 one = make_double2(1.0, 0.0);
+    return launch_sell<2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
+                          (const double2*)xin, (double2*)xout, one, one, nullptr, (const double2*)dinv, (const double2*)b,
+                          omega, (cudaStream_t)stream);
 }
 
 extern "C" int hx_sell_slice_widths(int n, const int32_t* indptr, const int32_t* row_perm, int n_slices,
@@ -318,11 +377,20 @@ extern "C" int hx_sell_slice_widths(int n, const int32_t* indptr, const int32_t*
 
 extern "C" int hx_sell_fill(int n, const int32_t* indptr, const int32_t* indices, const double* vals,
                             const int32_t* row_perm, int n_slices, const int64_t* slice_ptr, int32_t* cols,
-                            double* svals, hx_stream_t stream) {
+                            double* svals, int32_t* src, hx_stream_t stream) {
     if (n <= 0) return HX_OK;
     sell_fill_kernel<<<ceil_div(n_slices, 8), 256, 0, (cudaStream_t)stream>>>(
-        n, indptr, indices, (const double2*)vals, row_perm, n_slices, (const long long*)slice_ptr, cols, (double2*)svals);
+        n, indptr, indices, (const double2*)vals, row_perm, n_slices, (const long long*)slice_ptr, cols, (double2*)svals, src);
     return check_launch("sell_fill_kernel");
+}
+
+extern "C" int hx_sell_gather(int64_t total, const int32_t* src, const double* csr_vals, double* sell_vals,
+                              hx_stream_t stream) {
+    if (total <= 0) return HX_OK;
+    long long blocks = ceil_div<long long>(total, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    sell_gather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(total, src, (const double2*)csr_vals, (double2*)sell_vals);
+    return check_launch("sell_gather_kernel");
 }
 
 extern "C" int hx_combine_abc(int64_t nnz, const double* a, const double* b, const double* c, const double* ca_h,

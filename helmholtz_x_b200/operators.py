@@ -239,6 +239,7 @@ class ShiftedSolver:
         else:
             mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=self.P_values)
         self.mg = mg
+        self.Pop = mg.fine_operator() if len(mg.levels) > 1 else self.P
         ops.stats["shifts"] += 1
         n = ops.n
         self.basis = krylov.ArnoldiBasis(be, n, restart)
@@ -251,7 +252,7 @@ class ShiftedSolver:
             self._setup_woodbury()
 
     def _solve_P(self, b, x):
-        its, rel = krylov.gmres(self.be, lambda v, o: self.be.spmv(self.P, v, o), b, x, precond=self.mg.apply,
+        its, rel = krylov.gmres(self.be, lambda v, o: self.be.spmv(self.Pop, v, o), b, x, precond=self.mg.apply,
                                 rtol=self.rtol, restart=self.restart, maxiter=self.maxiter, basis=self.basis, work=self.work)
         self.ops.stats["inner_solves"] += 1
         self.ops.stats["inner_iterations"] += its

@@ -54,16 +54,28 @@ int hx_spmv_zz(int n, const int32_t* indptr, const int32_t* indices, const doubl
 int hx_spmv_dz(int n, const int32_t* indptr, const int32_t* indices, const double* vals_f64,
                const double* x_c128, double* y_c128, const double* alpha_c128_h,
                const double* beta_c128_h, const double* y0_c128, int lanes, hx_stream_t stream);
-/* sliced-ELL (C=32) variant of the complex SpMV; see hx_sell_* below */
+/* SELL-32-sigma variant (rows sorted by length in windows, 32-row slices stored
+ * column-major: fully coalesced, one thread per row).  y[row_perm[r]] = ...;
+ * alpha/beta/y0 as in hx_spmv_zz (all NULL => y = M x).  variant: 0 = default tuning,
+ * 1..5 = (unroll, min CTAs/SM) alternatives kept for the roofline study. */
 int hx_spmv_sell_zz(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols,
                     const double* vals_c128, const int32_t* row_perm, const double* x_c128,
-                    double* y_c128, hx_stream_t stream);
-/* CSR -> SELL-32 conversion helpers (slice widths, then fill) */
+                    double* y_c128, const double* alpha_c128_h, const double* beta_c128_h,
+                    const double* y0_c128, int variant, hx_stream_t stream);
+/* damped-Jacobi sweep on the SELL matrix: xout = xin + omega * dinv .* (b - M xin) */
+int hx_jacobi_sell(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols,
+                   const double* vals_c128, const int32_t* row_perm, const double* dinv_c128,
+                   const double* b_c128, const double* xin_c128, double* xout_c128, double omega,
+                   int variant, hx_stream_t stream);
+/* CSR -> SELL-32 conversion: slice widths, then fill (sell_vals and/or the
+ * sell-position -> csr-position map `src` may be NULL), then value refresh by gather */
 int hx_sell_slice_widths(int n, const int32_t* indptr, const int32_t* row_perm, int n_slices,
                          int32_t* widths, hx_stream_t stream);
 int hx_sell_fill(int n, const int32_t* indptr, const int32_t* indices, const double* vals_c128,
                  const int32_t* row_perm, int n_slices, const int64_t* slice_ptr, int32_t* cols,
-                 double* sell_vals_c128, hx_stream_t stream);
+                 double* sell_vals_c128, int32_t* src, hx_stream_t stream);
+int hx_sell_gather(int64_t total, const int32_t* src, const double* csr_vals_c128, double* sell_vals_c128,
+                   hx_stream_t stream);
 
 /* K8: P(sigma) = A + sigma B + sigma^2 C on the shared cell pattern, replacing the
  * MatAXPY chain of helmholtz_x/eigensolvers.py:174-176,240,309-315.  A, C real on

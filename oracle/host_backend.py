@@ -17,6 +17,7 @@ f64 = torch.float64
 
 class HostBackend:
     name = "host-test-double"
+    supports_sell = False
 
     def __init__(self):
         self.device = torch.device("cpu")

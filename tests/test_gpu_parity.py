@@ -201,9 +201,23 @@ def test_spmv_sell_matches_csr():
     x = be().asarray(rng.standard_normal(csr.n_cols) + 1j * rng.standard_normal(csr.n_cols), dtype=torch.complex128)
     y1, y2 = be().zeros(csr.n_rows), be().zeros(csr.n_rows)
     be().spmv(csr, x, y1)
-    sell.spmv(x, y2)
-    assert relmax(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-13
+    for variant in range(6):
+        y2.zero_()
+        sell.spmv(x, y2, variant=variant)
+        assert relmax(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-13
     assert sell.padding_ratio < 1.25
+    # alpha/beta epilogue and the Jacobi sweep on the SELL matrix against the CSR kernels
+    y0 = be().asarray(rng.standard_normal(csr.n_rows) + 0j, dtype=torch.complex128)
+    be().spmv(csr, x, y1, alpha=-1.0, beta=1.0, y0=y0)
+    be().spmv(sell, x, y2, alpha=-1.0, beta=1.0, y0=y0)
+    assert relmax(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-13
+    dinv = be().zeros(csr.n_rows)
+    be().diag_inv(csr, dinv)
+    be().jacobi_sweep(csr, dinv, y0, x, y1, 0.6)
+    be().jacobi_sweep(sell, dinv, y0, x, y2, 0.6)
+    assert relmax(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-13
+    be().jacobi_sweep(sell, dinv, y0, None, y2, 0.6)
+    assert relmax(y2.cpu().numpy(), (0.6 * dinv * y0).cpu().numpy()) < 1e-14
 
 
 def test_fused_operator_apply_with_flame_term():
