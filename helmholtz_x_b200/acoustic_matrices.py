@@ -71,19 +71,39 @@ class AcousticMatrices:
         self.impedance_terms = terms
 
         info("- Passive matrices are assembling..")
-        a_vals, c_vals = fem.assemble_AC(self.V, self.c)
+        part = mesh.partition()
+        if part is None:
+            Vasm, c_asm = self.V, self.c
+        else:
+            # multi-GPU: this rank assembles the cells touching its rows on its sub-mesh
+            if degree != 1:
+                raise NotImplementedError("multi-GPU runs support degree 1 (dof = mesh node) in this round")
+            from .dist import DistSpace
+            Vasm = fem.functionspace(part.local_mesh, ("Lagrange", 1))
+            cvals = np.real(self.c.x.array)
+            if isinstance(self.c.function_space, fem.DG0Space):
+                c_asm = fem.Function(fem.DG0Space(part.local_mesh), part.restrict_cell(cvals), dtype=np.float64)
+            else:
+                c_asm = fem.Function(Vasm, part.restrict_nodal(cvals[:mesh.n_nodes]), dtype=np.float64)
+            bc_dofs = [part.g2l[d][part.g2l[d] >= 0] for d in bc_dofs]
+        a_vals, c_vals = fem.assemble_AC(Vasm, c_asm)
         self.C_nobc_values = c_vals
         if bc_dofs:
             dofs = np.unique(np.concatenate(bc_dofs))
             self.bcs_Dirichlet = dofs
             self.C_nobc_values = c_vals.clone()
-            fem.apply_dirichlet(self.V, a_vals, dofs)
-            fem.apply_dirichlet(self.V, c_vals, dofs)
+            fem.apply_dirichlet(Vasm, a_vals, dofs)
+            fem.apply_dirichlet(Vasm, c_vals, dofs)
         info("- Matrix A is assembled.")
         b_vals = None
         if terms:
-            b_vals = fem.assemble_B(self.V, self.c, terms)
+            b_vals = fem.assemble_B(Vasm, c_asm, terms)
             info("- Matrix B is assembled.")
+        if part is not None:
+            self.V = DistSpace(part, Vasm)
+            a_vals, c_vals = self.V.own_values(a_vals), self.V.own_values(c_vals)
+            self.C_nobc_values = self.V.own_values(self.C_nobc_values)
+            b_vals = self.V.own_values(b_vals) if b_vals is not None else None
         self.ops = OperatorSet(self.V, a_vals, c_vals, b_vals)
         self._A = Mat(self.ops, {"A": 1.0})
         self._C = Mat(self.ops, {"C": 1.0})

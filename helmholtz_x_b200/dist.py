@@ -1,0 +1,257 @@
+"""Multi-GPU row partition: one process per GPU, rows (P1 dofs = mesh
+nodes) split into contiguous chunks of a locality ordering, the way PETSc splits
+ownership ranges across MPI ranks.  Each rank assembles the cells touching its rows on
+its own sub-mesh, so assembly needs no exchange.  Per operator apply there is ONE
+exchange step -- the packed halo of interface x entries (NCCL send/recv) -- and per
+orthogonalisation pass one all-reduce of the Gram column.  The preconditioner is
+block-Jacobi across GPUs: each rank runs its AMG cycle on its diagonal block.
+
+The same code runs over gloo with the CPU test double (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .backend import CsrMatrix
+
+c128 = torch.complex128
+
+
+def world_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def morton_keys_np(x, bits=16):
+    lo = x.min(axis=0)
+    ext = max(float((x.max(axis=0) - lo).max()), 1e-300)
+    q = np.minimum(((x - lo) / ext * (2 ** bits - 1)).astype(np.uint64), 2 ** bits - 1)
+    key = np.zeros(len(x), np.uint64)
+    for b in range(bits):
+        for d in range(3):
+            key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + d)
+    return key
+
+
+class Partition:
+    """Node ownership + this rank's sub-mesh numbering + the halo exchange plan."""
+
+    def __init__(self, x, cells, world, rank, ordering="input", facets=None):
+        n = x.shape[0]
+        self.world, self.rank, self.n_global = world, rank, n
+        if ordering == "morton":
+            perm = np.argsort(morton_keys_np(x), kind="stable")
+        else:
+            perm = np.arange(n)
+        owner = np.empty(n, np.int32)
+        owner[perm] = (np.arange(n, dtype=np.int64) * world // n).astype(np.int32)
+        self.owner = owner
+        own = np.flatnonzero(owner == rank)
+        cell_mask = (owner[cells] == rank).any(axis=1)
+        self.cell_ids = np.flatnonzero(cell_mask)
+        lc = cells[cell_mask]
+        nodes = np.unique(lc)
+        ghost = nodes[owner[nodes] != rank]
+        ghost = ghost[np.lexsort((ghost, owner[ghost]))]            # grouped by owner, ascending id
+        self.n_own, self.n_ghost = len(own), len(ghost)
+        self.l2g = np.concatenate([own, ghost]).astype(np.int64)
+        g2l = np.full(n, -1, np.int64)
+        g2l[self.l2g] = np.arange(len(self.l2g))
+        self.g2l = g2l
+        self.local_cells = g2l[lc].astype(np.int32)
+        if facets is not None and len(facets):
+            fmask = (owner[facets] == rank).any(axis=1)
+            self.facet_ids = np.flatnonzero(fmask)
+            self.local_facets = g2l[facets[fmask]].astype(np.int32)
+            assert self.local_facets.min(initial=0) >= 0
+        else:
+            self.facet_ids = np.zeros(0, np.int64)
+            self.local_facets = np.zeros((0, 3), np.int32)
+        # ---- halo plan: who needs which of my rows --------------------------------------
+        self.ghost_owner_counts = np.bincount(owner[ghost], minlength=world)
+        if world > 1:
+            all_ghosts = [None] * world
+            dist.all_gather_object(all_ghosts, ghost.astype(np.int64))
+            all_own_counts = [None] * world
+            dist.all_gather_object(all_own_counts, int(self.n_own))
+        else:
+            all_ghosts, all_own_counts = [ghost], [self.n_own]
+        self.own_counts = np.array(all_own_counts, np.int64)
+        send_idx, send_counts = [], np.zeros(world, np.int64)
+        for q in range(world):
+            if q == rank:
+                continue
+            gq = all_ghosts[q]
+            mine = gq[owner[gq] == rank]                              # in q's ghost order
+            send_idx.append(g2l[mine])
+            send_counts[q] = len(mine)
+        self.send_counts = send_counts
+        self.send_idx_h = np.concatenate(send_idx).astype(np.int64) if send_idx else np.zeros(0, np.int64)
+        self._dev = {}
+
+    @property
+    def n_loc(self):
+        return self.n_own + self.n_ghost
+
+    def neighbours(self):
+        return [q for q in range(self.world) if q != self.rank and (self.send_counts[q] or self.ghost_owner_counts[q])]
+
+    def _send_idx(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = torch.as_tensor(self.send_idx_h, device=device)
+        return self._dev[key]
+
+    def exchange(self, x_loc):
+        """Fill the ghost tail of x_loc (length n_loc, complex128) from the owners."""
+        if self.world == 1 or (self.n_ghost == 0 and self.send_idx_h.size == 0):
+            return x_loc
+        sendbuf = torch.view_as_real(x_loc[self._send_idx(x_loc.device)].contiguous())
+        ghost = torch.view_as_real(x_loc[self.n_own:])
+        ops, soff, roff = [], 0, 0
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            ns, nr = int(self.send_counts[q]), int(self.ghost_owner_counts[q])
+            if ns:
+                ops.append(dist.P2POp(dist.isend, sendbuf[soff:soff + ns], q))
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, ghost[roff:roff + nr], q))
+            soff += ns
+            roff += nr
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return x_loc
+
+    # ---- global <-> distributed host helpers -------------------------------------------
+    def restrict_nodal(self, arr):
+        return np.asarray(arr)[self.l2g]
+
+    def restrict_cell(self, arr):
+        return np.asarray(arr)[self.cell_ids]
+
+    def gather_global(self, x_own):
+        """All ranks get the global vector (host numpy) from the owned device pieces."""
+        if self.world == 1:
+            out = np.zeros(self.n_global, complex)
+            out[self.l2g[:self.n_own]] = x_own.cpu().numpy()
+            return out
+        mx = int(self.own_counts.max())
+        pad = torch.zeros(mx, 2, dtype=torch.float64, device=x_own.device)
+        pad[:self.n_own] = torch.view_as_real(x_own.contiguous())
+        bufs = [torch.zeros_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad)
+        ids = [None] * self.world
+        dist.all_gather_object(ids, self.l2g[:self.n_own])
+        out = np.zeros(self.n_global, complex)
+        for q in range(self.world):
+            v = bufs[q][:int(self.own_counts[q])].cpu().numpy()
+            out[ids[q]] = v[:, 0] + 1j * v[:, 1]
+        return out
+
+
+class DistMatrix:
+    """Owned rows of a distributed matrix: local CSR/SELL operator (n_own x n_loc)."""
+    is_dist = True
+
+    def __init__(self, part: Partition, local, be_local):
+        self.part, self.op = part, local
+        self.n_rows = self.n_cols = part.n_own
+        self.nnz = local.nnz
+        self._xbuf = None
+        self.be_local = be_local
+
+    @property
+    def shape(self):
+        return (self.n_rows, self.n_cols)
+
+    def xbuf(self):
+        if self._xbuf is None:
+            self._xbuf = self.be_local.zeros(self.part.n_loc)
+        return self._xbuf
+
+    def to_scipy_local(self):
+        return self.op.to_scipy()
+
+
+class DistBackend:
+    """Wraps the per-GPU backend: vectors hold owned entries; reductions are all-reduced,
+    SpMV on a DistMatrix does the halo exchange first.  Everything else is local."""
+    name = "dist"
+
+    def __init__(self, local, part: Partition):
+        self.local, self.part = local, part
+        self.device = local.device
+        self.supports_sell = getattr(local, "supports_sell", False)
+
+    def __getattr__(self, name):
+        return getattr(self.local, name)
+
+    def spmv(self, M, x, y, alpha=1.0, beta=None, y0=None, lanes=None):
+        if getattr(M, "is_dist", False):
+            xl = M.xbuf()
+            xl[:self.part.n_own].copy_(x[:self.part.n_own])
+            self.part.exchange(xl)
+            return self.local.spmv(M.op, xl, y, alpha=alpha, beta=beta, y0=y0)
+        return self.local.spmv(M, x, y, alpha=alpha, beta=beta, y0=y0, lanes=lanes)
+
+    def multi_dot(self, V, k, w, out, conj=True):
+        self.local.multi_dot(V, k, w, out, conj)
+        if self.part.world > 1:
+            dist.all_reduce(torch.view_as_real(out[:k]))
+        return out
+
+    def multi_axpy(self, V, k, h, w, hacc=None, nrm2=None):
+        self.local.multi_axpy(V, k, h, w, hacc=hacc, nrm2=nrm2)
+        if nrm2 is not None and self.part.world > 1:
+            dist.all_reduce(nrm2[:1])
+        return w
+
+    def lowrank_dots(self, lr, x, t, transpose=False):
+        self.local.lowrank_dots(lr, x, t)
+        if self.part.world > 1:
+            dist.all_reduce(torch.view_as_real(t[:max(lr.r, 1)]))
+        return t
+
+
+class DistSpace:
+    """What OperatorSet / AMG need from a function space, for the owned rows of a rank:
+    pattern of the owned rows (columns in local numbering), the diagonal block, coordinates."""
+
+    def __init__(self, part: Partition, Vloc):
+        self.part, self.Vloc = part, Vloc
+        self.local_be = Vloc.be
+        self.be = DistBackend(Vloc.be, part)
+        self.n = part.n_own
+        self.n_global = part.n_global
+        self.degree = Vloc.degree
+        ip, ix = Vloc.pattern()
+        self.nnz_own = int(ip[part.n_own])
+        self._pattern = (ip[:part.n_own + 1].contiguous(), ix[:self.nnz_own].contiguous())
+        self.dof_coords = Vloc.dof_coords[:part.n_own].contiguous()
+        mask = self._pattern[1] < part.n_own
+        self.diag_sel = torch.nonzero(mask).reshape(-1)
+        rows = torch.repeat_interleave(torch.arange(part.n_own, device=ip.device),
+                                       (self._pattern[0][1:] - self._pattern[0][:-1]).long())
+        counts = torch.bincount(rows[mask], minlength=part.n_own)
+        dptr = torch.zeros(part.n_own + 1, dtype=torch.int64, device=ip.device)
+        dptr[1:] = torch.cumsum(counts, 0)
+        self._diag_pattern = (dptr.to(torch.int32).contiguous(), self._pattern[1][mask].contiguous())
+
+    def pattern(self):
+        return self._pattern
+
+    def own_values(self, full_values):
+        return full_values[:self.nnz_own].contiguous()
+
+    def matrix(self, values):
+        local = CsrMatrix(self.part.n_own, self.part.n_loc, self._pattern[0], self._pattern[1], values)
+        return DistMatrix(self.part, local, self.local_be)
+
+    def diag_matrix(self, values):
+        return CsrMatrix(self.part.n_own, self.part.n_own, self._diag_pattern[0], self._diag_pattern[1],
+                         values[self.diag_sel].contiguous())

@@ -53,7 +53,7 @@ class _Handle:
 
     def _vector(self, X, i, vr):
         if vr is not None:
-            vr.setArray(X[i].cpu().numpy())
+            vr.setArray(self.K.ops.to_global(X[i].contiguous()))
 
     def getEigenvalue(self, i):
         return complex(self._eig[i])
@@ -103,7 +103,8 @@ class EPS(_Handle):
             be.spmv(Mcsr, v, tmp)
             solver.solve(tmp, out)
 
-        res = krylov.krylov_schur(be, op, n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit)
+        res = krylov.krylov_schur(be, op, n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit,
+                                  n_global=ops.n_global)
         self._eig = sigma + 1.0 / res.theta
         self._X, self._its, self._nconv = res.X, res.its, res.nconv
         self.stats = {"n_apply": res.n_apply, "residuals": res.residuals}
@@ -116,7 +117,8 @@ class EPS(_Handle):
                 be.spmv(Mcsr, v, tmp)
                 solver_t.solve(tmp, out)
 
-            rt = krylov.krylov_schur(be, op_t, n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit, seed=1)
+            rt = krylov.krylov_schur(be, op_t, n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit, seed=1,
+                                     n_global=ops.n_global)
             lam_t = sigma + 1.0 / rt.theta
             Y = be.zeros(len(self._eig), n)
             for i, lam in enumerate(self._eig):
@@ -167,16 +169,13 @@ class PEP(_Handle):
             out[n:].copy_(u)
             be.axpby(-sigma, p, 1.0, out[n:])             # out_bot = u + sigma * out_top
 
-        res = krylov.krylov_schur(be, op, 2 * n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit)
+        res = krylov.krylov_schur(be, op, 2 * n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit,
+                                  n_global=2 * ops.n_global)
         self._eig = sigma + 1.0 / res.theta
         self._X = res.X[:, :n]
         self._its, self._nconv = res.its, res.nconv
         self.stats = {"n_apply": res.n_apply, "residuals": res.residuals}
         return self
-
-    def _vector(self, X, i, vr):
-        if vr is not None:
-            vr.setArray(X[i].contiguous().cpu().numpy())
 
     def device_vector(self, i, which="right"):
         return self._X[i].contiguous()

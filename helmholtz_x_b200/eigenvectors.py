@@ -10,6 +10,16 @@ from .solver_utils import info, rank0
 
 def _mass_form(V, matrices, vec):
     """p^T M p with the UNCONJUGATED mass form p*p*dx (eigenvectors.py:47): SpMV + dot on the device."""
+    if matrices is not None and getattr(matrices, "ops", None) is not None and matrices.ops.part is not None:
+        # multi-GPU: mass matrix rows of this rank (no Dirichlet rows), dot all-reduced
+        ops = matrices.ops
+        be = ops.be
+        x = be.asarray(ops.to_local(np.asarray(vec, complex)), dtype=torch.complex128)
+        y = be.zeros(ops.n)
+        be.spmv(ops.space.matrix(matrices.C_nobc_values), x, y)
+        out = be.zeros(2)
+        be.multi_dot(x.view(1, -1), 1, y, out, conj=False)
+        return complex(out[0].cpu().numpy())
     be = V.be
     if not hasattr(V, "_mass"):
         ones = np.ones(V.mesh.n_nodes)
@@ -40,10 +50,10 @@ def normalize_eigenvector(mesh, obj, i, absolute=False, degree=1, which='right',
         omega = eig
     if BlochRemapper:
         vr = matrix_vector(BlochRemapper, vr)
-    if matrices:
+    if matrices and getattr(matrices.ops, "part", None) is None:
         V = matrices.V
     else:
-        V = functionspace(mesh, ("CG", degree))
+        V = functionspace(mesh, ("CG", degree))        # global container (multi-GPU: replicated host vector)
     p = Function(V)
     FixSign(vr)
     p.x.petsc_vec.setArray(vr.array)

@@ -85,6 +85,22 @@ class Mesh:
         self._facet_colors = {}
         self._volumes = None
         self._facet_cell = None
+        self._part = None
+
+    def partition(self):
+        """Row partition of this mesh over the process group (dist.Partition) with the
+        rank's sub-mesh attached as .local_mesh; None when running on one GPU."""
+        from . import dist as hxdist
+        world, rank = hxdist.world_info()
+        if world == 1:
+            return None
+        if self._part is None:
+            import os
+            part = hxdist.Partition(self.x, self.cells, world, rank, os.environ.get("HX_PARTITION", "morton"), self.facets)
+            part.local_mesh = Mesh(self.x[part.l2g], part.local_cells, self.cell_tags[part.cell_ids], part.local_facets,
+                                   self.facet_tags[part.facet_ids], backend=self.be)
+            self._part = part
+        return self._part
 
     # -- colouring (host integer preprocessing through the C-ABI) --------------------------
     @staticmethod

@@ -20,10 +20,13 @@ class FlameMatrix:
         self.degree = degree
         self.bloch_object = bloch_object
         self.tol = tol
-        self.V = fem.functionspace(mesh, ("Lagrange", degree))
+        # multi-GPU: this rank works on its sub-mesh and keeps the entries of the rows it owns
+        self.part = mesh.partition()
+        self.amesh = mesh if self.part is None else self.part.local_mesh
+        self.V = fem.functionspace(self.amesh, ("Lagrange", degree))
         self.gdim = 3
-        self.global_size = self.V.n
-        self.local_size = self.V.n
+        self.global_size = fem.functionspace(mesh, ("Lagrange", degree)).n if self.part is None else mesh.n_nodes
+        self.local_size = self.V.n if self.part is None else self.part.n_own
         self._D_ij = None
         self._D_ij_adj = None
         self._D = None
@@ -48,11 +51,23 @@ class FlameMatrix:
     def indices_and_values(self, dense):
         """Threshold |v| < tol -> 0 and compact to (dof, value) (flame_matrices.py:61-73)."""
         fem.threshold(self.V.be, dense, self.tol)
+        if self.part is not None:
+            dense = dense[:self.part.n_own]              # ghost rows are incomplete and belong to other ranks
         idx = torch.nonzero(dense).reshape(-1)
         return idx.cpu().numpy().astype(np.int32), dense[idx].cpu().numpy()
 
+    def _local(self, f):
+        """Coefficient restricted to this rank's sub-mesh (identity on one GPU)."""
+        if self.part is None or not isinstance(f, fem.Function):
+            return f
+        vals = np.real(f.x.array)
+        if isinstance(f.function_space, fem.DG0Space):
+            return fem.Function(fem.DG0Space(self.amesh), self.part.restrict_cell(vals), dtype=np.float64)
+        return fem.Function(fem.functionspace(self.amesh, ("Lagrange", 1)), self.part.restrict_nodal(vals[:self.mesh.n_nodes]),
+                            dtype=np.float64)
+
     def _set(self, lefts, rights, problem_type):
-        be, n = self.V.be, self.V.n
+        be, n = self.V.be, self.local_size
         lr = build_lowrank(be, n, lefts, rights)
         lr_T = build_lowrank(be, n, rights, lefts)
         if problem_type == 'direct':
@@ -90,26 +105,42 @@ class PointwiseFlameMatrix(FlameMatrix):
         self.subdomains = subdomains
 
     def _assemble_vectors(self, flame, point=None):
-        left = fem.flame_left(self.V, self.h, self.q_0 / self.u_b, gm1_const=self.gamma - 1, tag=flame)
+        left = fem.flame_left(self.V, self._local(self.h), self.q_0 / self.u_b, gm1_const=self.gamma - 1, tag=flame)
         return self.indices_and_values(left)
 
     def assemble_submatrices(self, problem_type='direct'):
         info("- Generating matrix D..")
         V = self.V
         pts = np.asarray(self.x_r, float).reshape(-1, 3)
-        owner, ptsd = fem.locate_points(self.mesh, pts, 1e-10)
-        dz = fem.point_dphidz(V, ptsd, owner).cpu().numpy()
-        owner_h = owner.cpu().numpy()
-        cell_dofs = V.cell_dofs[owner.clamp_max(self.mesh.n_cells - 1).long()].cpu().numpy()
+        amesh = self.amesh
+        owner, ptsd = fem.locate_points(amesh, pts, 1e-10)
+        owner_h = owner.cpu().numpy().astype(np.int64)
+        if self.part is not None:
+            # lowest GLOBAL cell index wins (same tie-break as one GPU); every rank that holds
+            # that cell evaluates it and keeps the entries of the rows it owns
+            import torch.distributed as tdist
+            none = np.iinfo(np.int64).max
+            gid = np.where(owner_h < amesh.n_cells, self.part.cell_ids[np.minimum(owner_h, amesh.n_cells - 1)], none)
+            gmin = torch.as_tensor(gid, device=owner.device)
+            tdist.all_reduce(gmin, op=tdist.ReduceOp.MIN)
+            gmin = gmin.cpu().numpy()
+            pos = np.searchsorted(self.part.cell_ids, gmin)
+            have = (pos < amesh.n_cells) & (self.part.cell_ids[np.minimum(pos, amesh.n_cells - 1)] == gmin)
+            owner_h = np.where(have, pos, amesh.n_cells)
+            owner = V.be.asarray(owner_h.astype(np.int32), dtype=torch.int32)
+        dz = fem.point_dphidz(V, ptsd, owner.clamp_max(amesh.n_cells - 1)).cpu().numpy()
+        cell_dofs = V.cell_dofs[owner.clamp_max(amesh.n_cells - 1).long()].cpu().numpy()
         lefts, rights = [], []
         for flame in range(len(pts)):
             lefts.append(self._assemble_vectors(flame))
-            if owner_h[flame] >= self.mesh.n_cells:
+            if owner_h[flame] >= amesh.n_cells:
                 rights.append((np.zeros(0, np.int32), np.zeros(0)))
             else:
                 vals = dz[flame] / self.rho_u
                 vals = np.where(np.abs(vals) < self.tol, 0.0, vals)
                 keep = vals != 0.0
+                if self.part is not None:
+                    keep &= cell_dofs[flame] < self.part.n_own
                 rights.append((cell_dofs[flame][keep].astype(np.int32), vals[keep]))
             info("- Matrix contribution of flame " + str(flame) + " is computed.")
         self._set(lefts, rights, problem_type)
@@ -127,11 +158,13 @@ class DistributedFlameMatrix(FlameMatrix):
 
     def _assemble_vectors(self, problem_type='direct'):
         if np.ndim(self.gamma) == 0 and not isinstance(self.gamma, fem.Function):
-            left = fem.flame_left(self.V, self.h, self.q_0 / self.u_b, gm1_const=float(self.gamma) - 1.0)
+            left = fem.flame_left(self.V, self._local(self.h), self.q_0 / self.u_b, gm1_const=float(self.gamma) - 1.0)
         else:
             g = self.gamma.x.array.real if isinstance(self.gamma, fem.Function) else np.asarray(self.gamma)
-            left = fem.flame_left(self.V, self.h, self.q_0 / self.u_b, gm1_nodal=g - 1.0)
-        right = fem.flame_right(self.V, self.w, self.rho)
+            if self.part is not None:
+                g = self.part.restrict_nodal(g[:self.mesh.n_nodes])
+            left = fem.flame_left(self.V, self._local(self.h), self.q_0 / self.u_b, gm1_nodal=g - 1.0)
+        right = fem.flame_right(self.V, self._local(self.w), self._local(self.rho))
         return self.indices_and_values(left), self.indices_and_values(right)
 
     def assemble_submatrices(self, problem_type='direct'):

@@ -173,18 +173,20 @@ class KrylovSchurResult:
         self.theta, self.X, self.its, self.nconv, self.residuals, self.n_apply = theta, X, its, nconv, residuals, n_apply
 
 
-def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, seed=0):
+def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, seed=0, n_global=None):
     """nev eigenpairs of largest |theta| of the operator apply_op(v, out) on C^n.
     SLEPc defaults: ncv = max(2 nev, nev+15) (eigensolvers.py:58 passes DECIDE),
     restart keeping half of the non-converged part."""
     import scipy.linalg as sla
     if ncv is None:
         ncv = max(2 * nev, nev + 15)
-    m = min(ncv, n - 1) if n > 2 else 1
+    ng = n_global if n_global is not None else n           # n = local (owned) length on multi-GPU runs
+    m = min(ncv, ng - 1) if ng > 2 else 1
     basis = ArnoldiBasis(be, n, m)
     V, w = basis.V, basis.w
     if v0 is None:
-        g = torch.Generator().manual_seed(seed)
+        part = getattr(be, "part", None)
+        g = torch.Generator().manual_seed(seed + (1000 * part.rank if part is not None else 0))
         v0 = torch.randn(n, dtype=torch.float64, generator=g).to(c128)
     v0 = be.asarray(v0, dtype=c128)
     nb = be.zeros(2)

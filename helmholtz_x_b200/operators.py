@@ -130,10 +130,10 @@ class Mat:
 
     # -- PETSc-like surface used by drivers / eigenvectors.py --------------------------------------
     def getSize(self):
-        return (self.ops.n, self.ops.n)
+        return (self.ops.n_global, self.ops.n_global)
 
     def createVecs(self):
-        return _Vec(np.zeros(self.ops.n, complex)), _Vec(np.zeros(self.ops.n, complex))
+        return _Vec(np.zeros(self.ops.n_global, complex)), _Vec(np.zeros(self.ops.n_global, complex))
 
     getVecs = createVecs
 
@@ -168,10 +168,10 @@ class Mat:
     def mult(self, x, y):
         """PETSc MatMult on host Vec wrappers (petsc4py_utils.py:86,96)."""
         be = self.ops.be
-        xd = be.asarray(np.asarray(x.array, complex), dtype=c128)
+        xd = be.asarray(self.ops.to_local(np.asarray(x.array, complex)), dtype=c128)
         yd = be.zeros(self.ops.n)
         self.apply(xd, yd)
-        y.setArray(yd.cpu().numpy())
+        y.setArray(self.ops.to_global(yd))
 
 
 class OperatorSet:
@@ -179,11 +179,14 @@ class OperatorSet:
 
     def __init__(self, space, a_vals, c_vals, b_vals=None):
         self.space, self.be, self.n = space, space.be, space.n
+        self.part = getattr(space, "part", None)                   # multi-GPU row partition (dist.DistSpace)
+        self.n_global = getattr(space, "n_global", space.n)
         self.base = {"A": a_vals, "C": c_vals, "B": b_vals, "Bh": torch.conj_physical(b_vals) if b_vals is not None else None}
         self._amg = None
         self._cache = {}
         self.amg_options = {}
-        self.stats = {"inner_solves": 0, "inner_iterations": 0, "amg_setups": 0, "shifts": 0}
+        self.stats = {"inner_solves": 0, "inner_iterations": 0, "amg_setups": 0, "shifts": 0,
+                      "t_amg_setup": 0.0, "t_shift": 0.0, "t_inner": 0.0}
 
     def combine(self, terms):
         key = tuple(sorted(terms.items()))
@@ -201,12 +204,38 @@ class OperatorSet:
             self._cache[key] = out
         return self._cache[key]
 
+    def to_local(self, global_host_array):
+        """Owned slice of a global host vector (identity on one GPU)."""
+        if self.part is None:
+            return global_host_array
+        return np.ascontiguousarray(global_host_array[self.part.l2g[:self.part.n_own]])
+
+    def to_global(self, local_device_vector):
+        """Global host vector from the owned device pieces (all ranks get it)."""
+        if self.part is None:
+            return local_device_vector.cpu().numpy()
+        return self.part.gather_global(local_device_vector)
+
     def amg(self):
+        if self._amg is None and self.part is not None:
+            # block-Jacobi across GPUs: each rank's hierarchy lives on its diagonal block
+            import time
+            t0 = time.perf_counter()
+            dm = self.space.diag_matrix
+            B = dm(self.base["B"]) if self.base["B"] is not None else None
+            self._amg = AMG(self.space.local_be, dm(self.base["A"]), dm(self.base["C"]), B, self.space.dof_coords,
+                            **self.amg_options)
+            self.stats["amg_setups"] += 1
+            self.stats["t_amg_setup"] += time.perf_counter() - t0
         if self._amg is None:
             pat = self.space.matrix
             B = pat(self.base["B"]) if self.base["B"] is not None else None
+            import time
+            t0 = time.perf_counter()
             self._amg = AMG(self.be, pat(self.base["A"]), pat(self.base["C"]), B, self.space.dof_coords, **self.amg_options)
+            self.be.synchronize()
             self.stats["amg_setups"] += 1
+            self.stats["t_amg_setup"] += time.perf_counter() - t0
         return self._amg
 
 
@@ -218,11 +247,14 @@ class ShiftedSolver:
         self.ops, self.be = ops, ops.be
         be = self.be
         self.rtol, self.restart, self.maxiter = rtol, restart, maxiter
+        import time
         t = dict(terms)
         use_bh = t.get("Bh", 0) != 0
+        mg = ops.amg()
+        t_shift0 = time.perf_counter()
         self.P_values = ops.combine(t)
         self.P = ops.space.matrix(self.P_values)
-        mg = ops.amg()
+        fine_vals = self.P_values if ops.part is None else self.P_values[ops.space.diag_sel].contiguous()
         if use_bh:
             # coarse B^H = conj(B_c): run the hierarchy on conjugated B
             for L in mg.levels:
@@ -232,15 +264,16 @@ class ShiftedSolver:
             for L in mg.levels:
                 if L.b is not None:
                     L.b = L.b_conj
-            mg.set_shift(t.get("A", 0), t.get("Bh", 0), t.get("C", 0), fine_values=self.P_values)
+            mg.set_shift(t.get("A", 0), t.get("Bh", 0), t.get("C", 0), fine_values=fine_vals)
             for L in mg.levels:
                 if L.b is not None:
                     L.b = L.b_direct
         else:
-            mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=self.P_values)
+            mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=fine_vals)
         self.mg = mg
-        self.Pop = mg.fine_operator() if len(mg.levels) > 1 else self.P
+        self.Pop = mg.fine_operator() if (len(mg.levels) > 1 and ops.part is None) else self.P
         ops.stats["shifts"] += 1
+        ops.stats["t_shift"] += time.perf_counter() - t_shift0
         n = ops.n
         self.basis = krylov.ArnoldiBasis(be, n, restart)
         self.work = be.zeros(n)
@@ -252,10 +285,13 @@ class ShiftedSolver:
             self._setup_woodbury()
 
     def _solve_P(self, b, x):
+        import time
+        t0 = time.perf_counter()
         its, rel = krylov.gmres(self.be, lambda v, o: self.be.spmv(self.Pop, v, o), b, x, precond=self.mg.apply,
                                 rtol=self.rtol, restart=self.restart, maxiter=self.maxiter, basis=self.basis, work=self.work)
         self.ops.stats["inner_solves"] += 1
         self.ops.stats["inner_iterations"] += its
+        self.ops.stats["t_inner"] += time.perf_counter() - t0
         if rel > max(self.rtol * 100, 1e-8):
             raise RuntimeError(f"inner GMRES stagnated: rel. residual {rel:.2e} after {its} iterations")
         return x

@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""One preconditioned inner solve (GMRES + SA-AMG V-cycle) on the synthetic annulus inside a
+cudaProfilerStart/Stop range, for `ncu --profile-from-start off` launch lists."""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dofs", type=int, default=1_000_000)
+    a = ap.parse_args()
+    import __graft_entry__ as ge
+    ge.build()
+    from helmholtz_x_b200 import fem
+    from helmholtz_x_b200.acoustic_matrices import AcousticMatrices
+    from helmholtz_x_b200.operators import ShiftedSolver
+    be = fem.default_backend()
+    g = bench.workload(a.dofs, 1)
+    mesh = fem.Mesh(g["x"], g["cells"], g["cell_tags"], g["facets"], g["facet_tags"])
+    c = fem.Function(fem.DG0Space(mesh), g["c"], dtype=np.float64, name="soundspeed")
+    with contextlib.redirect_stdout(io.StringIO()):
+        mats = AcousticMatrices(mesh, fem.MeshTags(mesh.facet_tags), {11: {"Robin": -0.875 - 0.2j}}, c, degree=1)
+    s = bench.TARGET
+    t0 = time.perf_counter()
+    solver = ShiftedSolver(mats.ops, {"A": 1.0, "B": s, "C": s ** 2})
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    n = mats.ops.n
+    b = torch.randn(n, dtype=torch.float64, device=be.device).to(torch.complex128)
+    x = be.zeros(n)
+    solver.solve(b, x)
+    torch.cuda.synchronize()
+    it0 = mats.ops.stats["inner_iterations"]
+    be.reset_launch_count()
+    torch.cuda.profiler.start()
+    t0 = time.perf_counter()
+    solver.solve(b, x)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    torch.cuda.profiler.stop()
+    its = mats.ops.stats["inner_iterations"] - it0
+    print(json.dumps({"n": n, "setup_s": round(t_setup, 3), "solve_s": round(dt, 4), "iterations": its,
+                      "ms_per_iteration": round(dt / its * 1e3, 4), "launches": be.launch_count(),
+                      "amg_sizes": solver.mg.sizes, "operator_complexity": round(solver.mg.operator_complexity, 3),
+                      "stats": mats.ops.stats}))
+
+
+if __name__ == "__main__":
+    main()
