@@ -227,6 +227,8 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     from helmholtz_x_b200.sell import SellMatrix
     csr = (mats.A + TARGET * mats.B + TARGET ** 2 * mats.C).csr()
+    if world > 1:
+        csr = csr.op                      # this rank's owned rows (n_own x n_loc)
     sell = SellMatrix.from_csr(be, csr)
     ms, nbytes = spmv_roofline(be, sell)
     ms_csr, _ = spmv_roofline(be, csr)

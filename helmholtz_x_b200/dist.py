@@ -49,6 +49,9 @@ class Partition:
         owner = np.empty(n, np.int32)
         owner[perm] = (np.arange(n, dtype=np.int64) * world // n).astype(np.int32)
         self.owner = owner
+        pos = np.empty(n, np.int64)
+        pos[perm] = np.arange(n, dtype=np.int64)
+        self.pos = pos                                  # rank of every node along the locality ordering
         own = np.flatnonzero(owner == rank)
         cell_mask = (owner[cells] == rank).any(axis=1)
         self.cell_ids = np.flatnonzero(cell_mask)
@@ -255,3 +258,72 @@ class DistSpace:
     def diag_matrix(self, values):
         return CsrMatrix(self.part.n_own, self.part.n_own, self._diag_pattern[0], self._diag_pattern[1],
                          values[self.diag_sel].contiguous())
+
+
+class CoarseCorrection:
+    """Global coarse space for the multi-GPU preconditioner: ~nc aggregates = equal runs of
+    the global locality (Morton) ordering, piecewise-constant prolongator P0.  The dense
+    coarse operators P0^T X P0 (X = A, B, C) are summed over ranks once per mesh; per shift
+    they are combined and inverted (replicated); per application: local restriction, one
+    all-reduce of nc complex numbers, dense GEMV, local prolongation.  Block-Jacobi AMG
+    alone misses the global low (indefinite) modes: measured on the 35 k-DoF annulus,
+    GMRES iterations 255 -> 81 (2 ranks) and 515 -> 114 (8 ranks) with nc = 1000."""
+
+    def __init__(self, space: "DistSpace", base, nc=1000):
+        part, be = space.part, space.local_be
+        self.part, self.be = part, be
+        dev = space._pattern[0].device
+        nc = int(min(nc, max(part.n_global // 8, 1)))
+        self.nc = nc
+        agg_loc = torch.as_tensor(part.pos[part.l2g] * nc // part.n_global, device=dev)
+        n_own = part.n_own
+        ip, ix = space._pattern
+        rows = torch.repeat_interleave(torch.arange(n_own, device=dev), (ip[1:] - ip[:-1]).long())
+        key = agg_loc[rows] * nc + agg_loc[ix.long()]
+        self._key = key
+        # P0 (n_own x nc) and R0 = P0^T (nc x n_own) as real CSR with unit entries
+        one = torch.ones(n_own, dtype=torch.float64, device=dev)
+        self.P0 = CsrMatrix(n_own, nc, torch.arange(n_own + 1, device=dev, dtype=torch.int32),
+                            agg_loc[:n_own].to(torch.int32).contiguous(), one)
+        order = torch.sort(agg_loc[:n_own], stable=True).indices
+        counts = torch.bincount(agg_loc[:n_own], minlength=nc)
+        rptr = torch.zeros(nc + 1, dtype=torch.int64, device=dev)
+        rptr[1:] = torch.cumsum(counts, 0)
+        self.R0 = CsrMatrix(nc, n_own, rptr.to(torch.int32).contiguous(), order.to(torch.int32).contiguous(), one)
+        self.dense = {}
+        for name in ("A", "B", "C", "Bh"):
+            v = base.get(name)
+            if v is None:
+                continue
+            self.dense[name] = self._galerkin(v.to(c128))
+        self.t = be.zeros(nc)
+        self.y = be.zeros(nc)
+        self.inv = None
+
+    def _galerkin(self, vals):
+        """sum_{i in I, j in J} a_ij over owned rows, all-reduced; deterministic (sort + segmented sum)."""
+        nc = self.nc
+        sp_ = torch.sparse_coo_tensor(self._key.view(1, -1), vals, size=(nc * nc,)).coalesce()
+        dense = torch.zeros(nc * nc, dtype=c128, device=vals.device)
+        dense[sp_.indices()[0]] = sp_.values()
+        if self.part.world > 1:
+            dist.all_reduce(torch.view_as_real(dense))
+        return dense.view(nc, nc)
+
+    def set_shift(self, terms):
+        M = torch.zeros(self.nc, self.nc, dtype=c128, device=self.t.device)
+        for k, v in terms.items():
+            if v != 0:
+                M += complex(v) * self.dense[k]
+        self.inv = M.t().contiguous()          # column-major view of M for the in-place inverse kernel
+        self.info = self.be.dense_inverse(self.inv)
+
+    def apply(self, v, x):
+        """x = P0 A0^-1 P0^T v  (v, x: owned entries)."""
+        be = self.be
+        be.spmv(self.R0, v, self.t)
+        if self.part.world > 1:
+            dist.all_reduce(torch.view_as_real(self.t))
+        be.dense_gemv(self.inv, self.t, self.y)
+        be.spmv(self.P0, self.y, x)
+        return x

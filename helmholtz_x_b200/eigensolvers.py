@@ -73,13 +73,21 @@ class _Handle:
     def device_vector(self, i, which="right"):
         return (self._X if which == "right" else self._Y)[i]
 
+    def start_vector(self):
+        """Sum of the computed Ritz vectors: a warm start for the next, nearby eigenproblem
+        of a fixed-point / Newton iteration (results do not depend on it)."""
+        X = getattr(self, "_Xfull", None)
+        X = X if X is not None else self._X
+        return None if X is None else X.sum(dim=0)
+
 
 class EPS(_Handle):
     """K x = lambda M x nearest the target, shift-invert Krylov-Schur (SLEPc EPS stand-in)."""
 
-    def __init__(self, K: Mat, M: Mat, target, nev, two_sided=False, tol=DEFAULT_TOL, ncv=None, maxit=100):
+    def __init__(self, K: Mat, M: Mat, target, nev, two_sided=False, tol=DEFAULT_TOL, ncv=None, maxit=100, v0=None):
         super().__init__()
         self.K, self.M, self.target, self.nev, self.two_sided = K, M, complex(target), nev, two_sided
+        self.v0 = v0
         self.tol, self.maxit = tol, maxit
         self.ncv = ncv or max(2 * nev, nev + 15)
 
@@ -104,7 +112,7 @@ class EPS(_Handle):
             solver.solve(tmp, out)
 
         res = krylov.krylov_schur(be, op, n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit,
-                                  n_global=ops.n_global)
+                                  n_global=ops.n_global, v0=self.v0)
         self._eig = sigma + 1.0 / res.theta
         self._X, self._its, self._nconv = res.X, res.its, res.nconv
         self.stats = {"n_apply": res.n_apply, "residuals": res.residuals}
@@ -134,9 +142,10 @@ class PEP(_Handle):
     shift-invert Krylov-Schur on the first companion linearisation,
     z=[u;v] -> [p; u + sigma p],  p = -P(sigma)^-1 (C v + (B + sigma C) u)."""
 
-    def __init__(self, K: Mat, B: Mat, C: Mat, target, nev, tol=DEFAULT_TOL, ncv=None, maxit=100):
+    def __init__(self, K: Mat, B: Mat, C: Mat, target, nev, tol=DEFAULT_TOL, ncv=None, maxit=100, v0=None):
         super().__init__()
         self.K, self.B, self.C, self.target, self.nev = K, B, C, complex(target), nev
+        self.v0 = v0
         self.tol, self.maxit = tol, maxit
         self.ncv = ncv or max(2 * nev, nev + 15)
 
@@ -170,8 +179,9 @@ class PEP(_Handle):
             be.axpby(-sigma, p, 1.0, out[n:])             # out_bot = u + sigma * out_top
 
         res = krylov.krylov_schur(be, op, 2 * n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit,
-                                  n_global=2 * ops.n_global)
+                                  n_global=2 * ops.n_global, v0=self.v0)
         self._eig = sigma + 1.0 / res.theta
+        self._Xfull = res.X
         self._X = res.X[:, :n]
         self._its, self._nconv = res.its, res.nconv
         self.stats = {"n_apply": res.n_apply, "residuals": res.residuals}
@@ -205,9 +215,10 @@ def results(E):
         print()
 
 
-def eps_solver(A, C, target, nev, two_sided=False, print_results=False):
-    """helmholtz_x/eigensolvers.py:41-67: A x = lambda (-C) x nearest target**2."""
-    E = EPS(A, -C, target ** 2, nev, two_sided=two_sided)
+def eps_solver(A, C, target, nev, two_sided=False, print_results=False, v0=None):
+    """helmholtz_x/eigensolvers.py:41-67: A x = lambda (-C) x nearest target**2.
+    v0 (extension): optional device start vector."""
+    E = EPS(A, -C, target ** 2, nev, two_sided=two_sided, v0=v0)
     info("- EPS solver started.")
     E.solve()
     info("- EPS solver converged. Eigenvalue computed.")
@@ -216,9 +227,10 @@ def eps_solver(A, C, target, nev, two_sided=False, print_results=False):
     return E
 
 
-def pep_solver(A, B, C, target, nev, print_results=False):
-    """helmholtz_x/eigensolvers.py:69-120: (A + w B + w^2 C) p = 0 nearest target."""
-    Q = PEP(A, B, C, target, nev)
+def pep_solver(A, B, C, target, nev, print_results=False, v0=None):
+    """helmholtz_x/eigensolvers.py:69-120: (A + w B + w^2 C) p = 0 nearest target.
+    v0 (extension): optional device start vector of length 2n."""
+    Q = PEP(A, B, C, target, nev, v0=v0)
     info("- PEP solver started.")
     Q.solve()
     info("- PEP solver converged. Eigenvalue computed.")
@@ -256,6 +268,7 @@ def fixed_point_iteration_eps(operators, D, target, nev=2, i=0, tol=1e-8, maxite
     info("-> Iterations are starting.\n ")
     while abs(domega) > tol:
         k += 1
+        v0 = E.start_vector()
         E.destroy()
         if rank0():
             print("* iter = {:2d}".format(k + 1))
@@ -270,7 +283,7 @@ def fixed_point_iteration_eps(operators, D, target, nev=2, i=0, tol=1e-8, maxite
             D_Mat = A - D_Mat
         else:
             D_Mat = A + (omega[k] * B) - D_Mat
-        E = eps_solver(D_Mat, C, target, nev, two_sided=two_sided, print_results=print_results)
+        E = eps_solver(D_Mat, C, target, nev, two_sided=two_sided, print_results=print_results, v0=v0)
         del D_Mat
         eig = E.getEigenvalue(i)
         f[k] = np.sqrt(eig)
@@ -304,6 +317,7 @@ def fixed_point_iteration_pep(operators, D, target, nev=2, i=0, tol=1e-8, maxite
     info("-> Fixed point iteration started.\n")
     while abs(domega) > tol:
         k += 1
+        v0 = E.start_vector()
         E.destroy()
         if rank0():
             print("* iter = {:2d}".format(k + 1))
@@ -315,7 +329,7 @@ def fixed_point_iteration_pep(operators, D, target, nev=2, i=0, tol=1e-8, maxite
         else:
             raise ValueError("The problem type should be specified as 'direct' or 'adjoint'.")
         D_Mat = A - D_Mat
-        E = pep_solver(D_Mat, B, C, target, nev, print_results=print_results)
+        E = pep_solver(D_Mat, B, C, target, nev, print_results=print_results, v0=v0)
         eig = E.getEigenpair(i)
         f[k] = eig
         if k != 0:

@@ -188,7 +188,7 @@ def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, 
         part = getattr(be, "part", None)
         g = torch.Generator().manual_seed(seed + (1000 * part.rank if part is not None else 0))
         v0 = torch.randn(n, dtype=torch.float64, generator=g).to(c128)
-    v0 = be.asarray(v0, dtype=c128)
+    v0 = be.asarray(v0, dtype=c128).clone()
     nb = be.zeros(2)
     be.multi_dot(v0.view(1, -1), 1, v0, nb)
     be.scale_copy(v0, V[0], alpha=1.0 / float(np.sqrt(nb[:1].cpu().numpy()[0].real)))

@@ -216,6 +216,13 @@ class OperatorSet:
             return local_device_vector.cpu().numpy()
         return self.part.gather_global(local_device_vector)
 
+    def coarse(self):
+        """Global coarse correction of the multi-GPU preconditioner (dist.CoarseCorrection)."""
+        if getattr(self, "_coarse", None) is None:
+            from .dist import CoarseCorrection
+            self._coarse = CoarseCorrection(self.space, self.base)
+        return self._coarse
+
     def amg(self):
         if self._amg is None and self.part is not None:
             # block-Jacobi across GPUs: each rank's hierarchy lives on its diagonal block
@@ -241,53 +248,82 @@ class OperatorSet:
 
 class ShiftedSolver:
     """x = (P + sum coef_k L_k R_k^T)^{-1} b,  P = sum terms*base  -- GMRES preconditioned
-    by the SA-AMG V-cycle for P, Woodbury for the flame terms (hard part 2)."""
+    by the SA-AMG V-cycle for P, Woodbury for the flame terms (hard part 2).
+
+    The state that depends only on P (level operators, coarse inverse, and the solves
+    Zbase = P^-1 L of the Woodbury update) is cached on the OperatorSet: in the fixed-point
+    iteration the shift is the same for every iterate (only FTF(omega_k) changes), so the
+    r extra solves are paid once per target instead of once per iterate."""
 
     def __init__(self, ops: OperatorSet, terms, lowrank=(), rtol=1e-11, restart=40, maxiter=400, transposed=False):
+        import time
+        if ops.part is not None:
+            restart, maxiter = 80, 800          # the two-level Schwarz preconditioner needs more iterations
         self.ops, self.be = ops, ops.be
         be = self.be
         self.rtol, self.restart, self.maxiter = rtol, restart, maxiter
-        import time
-        t = dict(terms)
-        use_bh = t.get("Bh", 0) != 0
+        t = {k: complex(v) for k, v in terms.items() if v != 0}
+        key = tuple(sorted(t.items()))
         mg = ops.amg()
-        t_shift0 = time.perf_counter()
-        self.P_values = ops.combine(t)
-        self.P = ops.space.matrix(self.P_values)
-        fine_vals = self.P_values if ops.part is None else self.P_values[ops.space.diag_sel].contiguous()
-        if use_bh:
-            # coarse B^H = conj(B_c): run the hierarchy on conjugated B
-            for L in mg.levels:
-                if L.b is not None and not hasattr(L, "b_direct"):
-                    L.b_direct = L.b
-                    L.b_conj = torch.conj_physical(L.b)
-            for L in mg.levels:
-                if L.b is not None:
-                    L.b = L.b_conj
-            mg.set_shift(t.get("A", 0), t.get("Bh", 0), t.get("C", 0), fine_values=fine_vals)
-            for L in mg.levels:
-                if L.b is not None:
-                    L.b = L.b_direct
-        else:
-            mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=fine_vals)
+        st = getattr(ops, "_shift_state", None)
+        if st is None or st["key"] != key:
+            t_shift0 = time.perf_counter()
+            use_bh = t.get("Bh", 0) != 0
+            P_values = ops.combine(t)
+            P = ops.space.matrix(P_values)
+            fine_vals = P_values if ops.part is None else P_values[ops.space.diag_sel].contiguous()
+            if use_bh:
+                # coarse B^H = conj(B_c): run the hierarchy on conjugated B
+                for L in mg.levels:
+                    if L.b is not None and not hasattr(L, "b_direct"):
+                        L.b_direct = L.b
+                        L.b_conj = torch.conj_physical(L.b)
+                for L in mg.levels:
+                    if L.b is not None:
+                        L.b = L.b_conj
+                mg.set_shift(t.get("A", 0), t.get("Bh", 0), t.get("C", 0), fine_values=fine_vals)
+                for L in mg.levels:
+                    if L.b is not None:
+                        L.b = L.b_direct
+            else:
+                mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=fine_vals)
+            Pop = mg.fine_operator() if (len(mg.levels) > 1 and ops.part is None) else P
+            if ops.part is not None:
+                ops.coarse().set_shift(t)
+            st = {"key": key, "P_values": P_values, "P": P, "Pop": Pop, "wood": {},
+                  "basis": krylov.ArnoldiBasis(be, ops.n, restart), "work": be.zeros(ops.n),
+                  "xc": be.zeros(ops.n), "r": be.zeros(ops.n)}
+            ops._shift_state = st
+            ops.stats["shifts"] += 1
+            ops.stats["t_shift"] += time.perf_counter() - t_shift0
+        self.st = st
         self.mg = mg
-        self.Pop = mg.fine_operator() if (len(mg.levels) > 1 and ops.part is None) else self.P
-        ops.stats["shifts"] += 1
-        ops.stats["t_shift"] += time.perf_counter() - t_shift0
-        n = ops.n
-        self.basis = krylov.ArnoldiBasis(be, n, restart)
-        self.work = be.zeros(n)
+        self.P_values, self.P, self.Pop = st["P_values"], st["P"], st["Pop"]
+        self.basis, self.work = st["basis"], st["work"]
         self.lowrank = [m for m in lowrank if m.coef != 0 and m.lr.r > 0]
         if transposed:
             self.lowrank = [m.transpose() for m in self.lowrank]
-        self.Z = []
         if self.lowrank:
             self._setup_woodbury()
+
+    def _precond(self, v, out):
+        """One GPU: the AMG V-cycle.  Multi-GPU: global coarse correction, then the rank-local
+        AMG cycle on the updated residual (two-level multiplicative Schwarz)."""
+        if self.ops.part is None:
+            return self.mg.apply(v, out)
+        cc = self.ops.coarse()
+        be = self.be
+        xc, r = self.st["xc"], self.st["r"]
+        cc.apply(v, xc)
+        be.spmv(self.Pop, xc, r, alpha=-1.0, beta=1.0, y0=v)          # r = v - P xc (halo exchange inside)
+        self.mg.apply(r, out)
+        be.axpby(1.0, xc, 1.0, out)
+        return out
 
     def _solve_P(self, b, x):
         import time
         t0 = time.perf_counter()
-        its, rel = krylov.gmres(self.be, lambda v, o: self.be.spmv(self.Pop, v, o), b, x, precond=self.mg.apply,
+        its, rel = krylov.gmres(self.be, lambda v, o: self.be.spmv(self.Pop, v, o), b, x, precond=self._precond,
                                 rtol=self.rtol, restart=self.restart, maxiter=self.maxiter, basis=self.basis, work=self.work)
         self.ops.stats["inner_solves"] += 1
         self.ops.stats["inner_iterations"] += its
@@ -297,31 +333,39 @@ class ShiftedSolver:
         return x
 
     def _setup_woodbury(self):
-        """(P - U W^T)^-1 with U = -coef*L (n x r dense), W = R: Z = P^-1 U, S = I - W^T Z."""
+        """(P - U W^T)^-1 with U = -L diag(coef) (n x r), W = R:
+        Zbase = P^-1 L (cached per shift), S = I - W^T Z = I + (W^T Zbase) diag(coef)."""
         be, n = self.be, self.ops.n
+        wkey = tuple(id(m.lr) for m in self.lowrank)
         r_tot = sum(m.lr.r for m in self.lowrank)
-        self.Zmat = be.zeros(r_tot, n)
-        u = be.zeros(n)
-        col = 0
-        for m in self.lowrank:
-            for f in range(m.lr.r):
-                u.zero_()
+        cache = self.st["wood"].get(wkey)
+        if cache is None:
+            Zbase = be.zeros(r_tot, n)
+            u = be.zeros(n)
+            col = 0
+            for m in self.lowrank:
                 e = be.zeros(m.lr.r)
-                e[f] = 1.0
-                be.lowrank_update(m.lr, e, -m.coef, u)          # u = -coef * left_f
-                self._solve_P(u, self.Zmat[col])
-                col += 1
-        S = np.eye(r_tot, dtype=complex)
-        row = 0
-        t = be.zeros(max(max(m.lr.r for m in self.lowrank), 1))
-        for m in self.lowrank:
-            for cz in range(r_tot):
-                be.lowrank_dots(m.lr, self.Zmat[cz], t)
-                S[row:row + m.lr.r, cz] -= t[:m.lr.r].cpu().numpy()
-            row += m.lr.r
-        self.S_inv = np.linalg.inv(S)
+                for f in range(m.lr.r):
+                    u.zero_()
+                    e.zero_()
+                    e[f] = 1.0
+                    be.lowrank_update(m.lr, e, 1.0, u)              # u = left_f
+                    self._solve_P(u, Zbase[col])
+                    col += 1
+            Sbase = np.zeros((r_tot, r_tot), complex)
+            row = 0
+            t = be.zeros(max(max(m.lr.r for m in self.lowrank), 1))
+            for m in self.lowrank:
+                for cz in range(r_tot):
+                    be.lowrank_dots(m.lr, Zbase[cz], t)
+                    Sbase[row:row + m.lr.r, cz] = t[:m.lr.r].cpu().numpy()
+                row += m.lr.r
+            cache = (Zbase, Sbase, t)
+            self.st["wood"] = {wkey: cache}                          # keep one entry: bounded memory
+        self.Zbase, Sbase, self._t = cache
+        self.coefs = np.concatenate([np.full(m.lr.r, m.coef) for m in self.lowrank])
+        self.S_inv = np.linalg.inv(np.eye(r_tot, dtype=complex) + Sbase * self.coefs[None, :])
         self.r_tot = r_tot
-        self._t = t
 
     def solve(self, b, x):
         self._solve_P(b, x)
@@ -334,5 +378,6 @@ class ShiftedSolver:
                 wt[row:row + m.lr.r] = self._t[:m.lr.r].cpu().numpy()
                 row += m.lr.r
             cvec = self.S_inv @ wt
-            be.multi_axpy(self.Zmat, self.r_tot, be.asarray(-cvec, dtype=c128), x)
+            # x += Z cvec with Z = -Zbase diag(coef)  <=>  x -= sum_j (coef_j cvec_j) Zbase_j
+            be.multi_axpy(self.Zbase, self.r_tot, be.asarray(self.coefs * cvec, dtype=c128), x)
         return x
