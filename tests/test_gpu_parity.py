@@ -401,6 +401,32 @@ def test_fpi_rijkeffd_config5_eigenpair_matches_golden():
     assert abs(E2.getEigenpair(0) - g) / abs(g) < EIG_RTOL
 
 
+def test_normalize_adjoint_config5_self_check():
+    """a13: eigenvectors.py:125-177; the reference prints '! Normalization Check:' = 1
+    (RijkeFFD/Results/ShapeDerivatives/results.log:113)."""
+    from helmholtz_x_b200.eigenvectors import normalize_adjoint, normalize_eigenvector
+    from helmholtz_x_b200.petsc4py_utils import vector_matrix_vector
+    case = cases.rijkeffd()
+    mats, D, E = _run_fpi(case)
+    omega_dir, p_dir = normalize_eigenvector(mats.mesh, E, 0, degree=1, which='right', matrices=mats, print_eigs=False)
+    _, _, E2 = _run_fpi(case, "adjoint")
+    omega_adj, p_adj = normalize_eigenvector(mats.mesh, E2, 0, degree=1, which='right', matrices=mats, print_eigs=False)
+    D.assemble_submatrices('direct')
+    p_adj_n = normalize_adjoint(omega_dir, p_dir, p_adj, mats, D)
+    dL = mats.B + mats.C * (2 * omega_dir) - D.get_derivative(omega_dir)
+    check = vector_matrix_vector(p_adj_n.x.petsc_vec, dL, p_dir.x.petsc_vec)
+    assert abs(check - 1.0) < 1e-10
+    # against the oracle's normalisation of its own eigenvectors (sign-fixed, so comparable)
+    ops, fl = cases.oracle_operators(case), cases.oracle_flame(case)
+    Eo, _ = ox.fixed_point_iteration(ops, fl, case.target, nev=2, i=0)
+    Ea, _ = ox.fixed_point_iteration(ops, fl, case.target, nev=2, i=0, problem_type="adjoint")
+    _, po = ox.normalize_eigenvector(ops, Eo, 0)
+    _, pa = ox.normalize_eigenvector(ops, Ea, 0)
+    pan, chk = ox.normalize_adjoint(ops, Eo.omega(0), po, pa, fl)
+    assert abs(chk - 1.0) < 1e-10
+    assert relmax(np.abs(p_adj_n.x.array), np.abs(pan)) < 1e-6
+
+
 def test_fpi_annulus_config3_matches_golden():
     """.../fullAnnulus/Results/Active/FPI/active.log:43-92 and eigenvalues_dir.txt"""
     case = cases.annulus()
