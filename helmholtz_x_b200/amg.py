@@ -51,8 +51,39 @@ def _from_coo(T) -> CsrMatrix:
                      T.values().contiguous())
 
 
+#: cuSPARSE SpGEMM (behind torch.sparse.mm) fails with "insufficient resources" once the number
+#: of intermediate products gets large (seen at 10 M DoF); the left operand is therefore
+#: processed in row blocks bounded by this many estimated products.
+_SPMM_MAX_PRODUCTS = 3.0e8
+
+
 def _spmm(A, B):
-    return torch.sparse.mm(A, B).coalesce()
+    A = A.coalesce()
+    B = B.coalesce()
+    nA, nB = A._nnz(), B._nnz()
+    est = float(nA) * (float(nB) / max(B.shape[0], 1))
+    if est <= _SPMM_MAX_PRODUCTS or A.shape[0] < 2:
+        return torch.sparse.mm(A, B).coalesce()
+    nblk = int(min(A.shape[0], np.ceil(est / _SPMM_MAX_PRODUCTS)))
+    rows = A.indices()[0]
+    bounds = torch.linspace(0, A.shape[0], nblk + 1, device=rows.device).long()
+    cut = torch.searchsorted(rows, bounds)            # coalesced => rows sorted
+    idx_out, val_out = [], []
+    for b in range(nblk):
+        lo, hi = int(cut[b]), int(cut[b + 1])
+        if hi == lo:
+            continue
+        r0, r1 = int(bounds[b]), int(bounds[b + 1])
+        sub_idx = A.indices()[:, lo:hi].clone()
+        sub_idx[0] -= r0
+        sub = torch.sparse_coo_tensor(sub_idx, A.values()[lo:hi], size=(r1 - r0, A.shape[1])).coalesce()
+        Cb = torch.sparse.mm(sub, B).coalesce()
+        ci = Cb.indices().clone()
+        ci[0] += r0
+        idx_out.append(ci)
+        val_out.append(Cb.values())
+        del Cb, sub
+    return torch.sparse_coo_tensor(torch.cat(idx_out, 1), torch.cat(val_out), size=(A.shape[0], B.shape[1])).coalesce()
 
 
 def _diag(M: CsrMatrix):

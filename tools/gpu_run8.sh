@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+bash tools/gpu_sweep.sh
+timeout 1500 python bench.py --steps 1 --warmup 0 --dofs 10000000 --spmv-dofs 0 --no-cpu-baseline > gpurun_out/bench_10M.json 2> gpurun_out/bench_10M.err
+echo "exit $?" >> gpurun_out/bench_10M.err
+cat gpurun_out/bench_10M.json | cut -c1-1500; grep -v "Warn\|sparse_coo" gpurun_out/bench_10M.err | tail -5 | cut -c1-300
