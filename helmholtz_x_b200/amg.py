@@ -121,7 +121,7 @@ class Level:
 
 
 class AMG:
-    def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=8,
+    def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=16,
                  coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=20000):
         """A, C real-valued, B complex or None -- all on ONE shared fine pattern."""
         self.be, self.nu, self.omega = be, nu, omega
@@ -168,13 +168,24 @@ class AMG:
                 v = v / rho
             ST = _spmm(S, T)
             Pm = (T - (4.0 / (3.0 * rho)) * ST).coalesce()
+            del K, S, ST, T, v
             Rm = Pm.t().coalesce()
-            Ac = _spmm(Rm, _spmm(_to_coo(pat, a_re), Pm))
-            Cc = _spmm(Rm, _spmm(_to_coo(pat, c_re), Pm))
+
+            def galerkin(vals):
+                X = _to_coo(pat, vals)
+                Y = _spmm(X, Pm)
+                del X
+                Z = _spmm(Rm, Y)
+                del Y
+                if vals.is_cuda:
+                    torch.cuda.empty_cache()      # the SpGEMM temporaries are GBs at 10 M DoF
+                return Z
+            Ac = galerkin(a_re)
+            Cc = galerkin(c_re)
             mats = [Ac, Cc]
             if b_cx is not None:
-                Br = _spmm(Rm, _spmm(_to_coo(pat, b_cx.real.contiguous()), Pm))
-                Bi = _spmm(Rm, _spmm(_to_coo(pat, b_cx.imag.contiguous()), Pm))
+                Br = galerkin(b_cx.real.contiguous())
+                Bi = galerkin(b_cx.imag.contiguous())
                 mats += [Br, Bi]
             keys = torch.unique(torch.cat([m.indices()[0] * nc + m.indices()[1] for m in mats]))
             crow, ccol = keys // nc, keys % nc
