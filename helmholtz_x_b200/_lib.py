@@ -35,6 +35,12 @@ SIGNATURES = {
     "hx_sell_slice_widths": [i32, vp, vp, i32, vp, vp],
     "hx_sell_fill": [i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "hx_sell_gather": [i64, vp, vp, vp, vp],
+    "hx_spmv_cc": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "hx_spmv_sc": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "hx_spmv_sell_cc": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "hx_jacobi_sell_c": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp],
+    "hx_jacobi_sweep_c": [i32, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp],
+    "hx_sell_gather_c": [i64, vp, vp, vp, vp],
     "hx_combine_abc": [i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_lowrank_dots": [i32, vp, vp, vp, vp, vp, vp],
     "hx_lowrank_update": [i32, vp, vp, vp, vp, vp, vp, vp, vp],

@@ -85,6 +85,7 @@ class LowRank:
 class CudaBackend:
     name = "cuda"
     supports_sell = True
+    supports_mixed = True        # complex64 kernels for the multigrid cycle
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():
@@ -122,9 +123,14 @@ class CudaBackend:
         """y = alpha*M@x (+ beta*y0)."""
         if getattr(M, "is_sell", False):
             return M.spmv(x, y, alpha=None if (alpha == 1.0 and beta is None) else alpha, beta=beta, y0=y0)
-        assert x.dtype == c128 and y.dtype == c128 and x.is_contiguous() and y.is_contiguous()
+        assert x.dtype == y.dtype and x.is_contiguous() and y.is_contiguous()
         assert x.numel() >= M.n_cols and y.numel() >= M.n_rows
-        name = "hx_spmv_zz" if M.values.dtype == c128 else "hx_spmv_dz"
+        if x.dtype == torch.complex64:
+            name = "hx_spmv_cc" if M.values.dtype == torch.complex64 else "hx_spmv_sc"
+            assert M.values.dtype in (torch.complex64, torch.float32)
+        else:
+            assert x.dtype == c128 and M.values.dtype in (c128, f64)
+            name = "hx_spmv_zz" if M.values.dtype == c128 else "hx_spmv_dz"
         y0p = None
         if beta is not None:
             y0p = (y0 if y0 is not None else y).data_ptr()
@@ -196,13 +202,14 @@ class CudaBackend:
 
     def jacobi_sweep(self, M, dinv, b, xin, xout, omega):
         """xout = xin + omega*dinv*(b - M xin); xin None => xout = omega*dinv*b (matrix unused)."""
+        name = "hx_jacobi_sweep_c" if b.dtype == torch.complex64 else "hx_jacobi_sweep"
         if xin is None:
-            _lib.call("hx_jacobi_sweep", M.n_rows, None, None, None, dinv.data_ptr(), b.data_ptr(), None, xout.data_ptr(),
+            _lib.call(name, M.n_rows, None, None, None, dinv.data_ptr(), b.data_ptr(), None, xout.data_ptr(),
                       float(omega), 8, self.stream)
         elif getattr(M, "is_sell", False):
             M.jacobi(dinv, b, xin, xout, omega)
         else:
-            _lib.call("hx_jacobi_sweep", M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(),
+            _lib.call(name, M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(),
                       dinv.data_ptr(), b.data_ptr(), xin.data_ptr(), xout.data_ptr(), float(omega), M.lanes, self.stream)
         return xout
 

@@ -64,6 +64,38 @@ __host__ __device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
 }
 inline double2 h2c(const double* p) { return make_double2(p[0], p[1]); }
 
+// ---- complex64 (float2) overloads: the mixed-precision multigrid cycle ---------------
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cscale(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
+__device__ __forceinline__ void cfma(float2& acc, float2 a, float2 b) {
+    acc.x = fmaf(a.x, b.x, acc.x);
+    acc.x = fmaf(-a.y, b.y, acc.x);
+    acc.y = fmaf(a.x, b.y, acc.y);
+    acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void rfma(float2& acc, float a, float2 b) {
+    acc.x = fmaf(a, b.x, acc.x);
+    acc.y = fmaf(a, b.y, acc.y);
+}
+// generic multiply-accumulate picked by the matrix value type
+__device__ __forceinline__ void mac(double2& acc, double2 a, double2 x) { cfma(acc, a, x); }
+__device__ __forceinline__ void mac(double2& acc, double a, double2 x) { rfma(acc, a, x); }
+__device__ __forceinline__ void mac(float2& acc, float2 a, float2 x) { cfma(acc, a, x); }
+__device__ __forceinline__ void mac(float2& acc, float a, float2 x) { rfma(acc, a, x); }
+template <typename V> __device__ __forceinline__ V vzero();
+template <> __device__ __forceinline__ double2 vzero<double2>() { return make_double2(0.0, 0.0); }
+template <> __device__ __forceinline__ float2 vzero<float2>() { return make_float2(0.f, 0.f); }
+template <typename V> struct scalar_of;
+template <> struct scalar_of<double2> { typedef double type; };
+template <> struct scalar_of<float2> { typedef float type; };
+template <typename V> __host__ __device__ __forceinline__ V from_c128(double2 z);
+template <> __host__ __device__ __forceinline__ double2 from_c128<double2>(double2 z) { return z; }
+template <> __host__ __device__ __forceinline__ float2 from_c128<float2>(double2 z) { return make_float2((float)z.x, (float)z.y); }
+
 // ---- streaming (read-once) loads: keep matrix streams out of L1 so the gathered
 // x vector stays cached (guide: ld.global.nc.L1::no_allocate) -------------------
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
@@ -74,6 +106,16 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
 __device__ __forceinline__ double ld_stream(const double* p) {
     double r;
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ int ld_stream(const int* p) {

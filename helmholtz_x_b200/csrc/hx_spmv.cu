@@ -6,54 +6,26 @@
 namespace hx {
 
 // ---- one row's dot product with LANES cooperating threads --------------------
-template <int LANES>
-__device__ __forceinline__ double2 row_dot(const int* __restrict__ indices, const double2* __restrict__ vals,
-                                           const double2* __restrict__ x, int start, int end, int lane) {
-    double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+// MV: matrix value type (double2 | double | float2 | float), V: vector type (double2 | float2)
+template <int LANES, typename MV, typename V>
+__device__ __forceinline__ V row_dot(const int* __restrict__ indices, const MV* __restrict__ vals,
+                                     const V* __restrict__ x, int start, int end, int lane) {
+    V acc0 = vzero<V>(), acc1 = vzero<V>();
     int k = start + lane;
     for (; k + LANES < end; k += 2 * LANES) {
         const int c0 = ld_stream(indices + k);
         const int c1 = ld_stream(indices + k + LANES);
-        const double2 v0 = ld_stream(vals + k);
-        const double2 v1 = ld_stream(vals + k + LANES);
-        const double2 x0 = __ldg(x + c0);
-        const double2 x1 = __ldg(x + c1);
-        cfma(acc0, v0, x0);
-        cfma(acc1, v1, x1);
+        const MV v0 = ld_stream(vals + k);
+        const MV v1 = ld_stream(vals + k + LANES);
+        const V x0 = __ldg(x + c0);
+        const V x1 = __ldg(x + c1);
+        mac(acc0, v0, x0);
+        mac(acc1, v1, x1);
     }
     if (k < end) {
         const int c0 = ld_stream(indices + k);
-        const double2 v0 = ld_stream(vals + k);
-        cfma(acc0, v0, __ldg(x + c0));
-    }
-    acc0 = cadd(acc0, acc1);
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-        acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, o, LANES);
-        acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, o, LANES);
-    }
-    return acc0;
-}
-
-template <int LANES>
-__device__ __forceinline__ double2 row_dot(const int* __restrict__ indices, const double* __restrict__ vals,
-                                           const double2* __restrict__ x, int start, int end, int lane) {
-    double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-    int k = start + lane;
-    for (; k + LANES < end; k += 2 * LANES) {
-        const int c0 = ld_stream(indices + k);
-        const int c1 = ld_stream(indices + k + LANES);
-        const double v0 = ld_stream(vals + k);
-        const double v1 = ld_stream(vals + k + LANES);
-        const double2 x0 = __ldg(x + c0);
-        const double2 x1 = __ldg(x + c1);
-        rfma(acc0, v0, x0);
-        rfma(acc1, v1, x1);
-    }
-    if (k < end) {
-        const int c0 = ld_stream(indices + k);
-        const double v0 = ld_stream(vals + k);
-        rfma(acc0, v0, __ldg(x + c0));
+        const MV v0 = ld_stream(vals + k);
+        mac(acc0, v0, __ldg(x + c0));
     }
     acc0 = cadd(acc0, acc1);
 #pragma unroll
@@ -66,42 +38,43 @@ __device__ __forceinline__ double2 row_dot(const int* __restrict__ indices, cons
 
 constexpr int kSpmvThreads = 256;
 
-template <int LANES, typename VT>
+template <int LANES, typename VT, typename V = double2>
 __global__ void __launch_bounds__(kSpmvThreads)
 spmv_csr_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
-                const VT* __restrict__ vals, const double2* __restrict__ x, double2* __restrict__ y,
-                double2 alpha, double2 beta, const double2* y0) {
+                const VT* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
+                V alpha, V beta, const V* y0) {
     const int row = blockIdx.x * (kSpmvThreads / LANES) + threadIdx.x / LANES;
     const int lane = threadIdx.x % LANES;
     const bool valid = row < n;   // no early exit: every lane reaches the full-mask shuffles
     const int start = valid ? __ldg(indptr + row) : 0, end = valid ? __ldg(indptr + row + 1) : 0;
-    double2 acc = row_dot<LANES>(indices, vals, x, start, end, lane);
+    V acc = row_dot<LANES, VT, V>(indices, vals, x, start, end, lane);
     if (valid && lane == 0) {
-        double2 r = cmul(alpha, acc);
+        V r = cmul(alpha, acc);
         if (y0) r = cadd(r, cmul(beta, y0[row]));
         y[row] = r;
     }
 }
 
-template <int LANES>
+template <int LANES, typename V = double2>
 __global__ void __launch_bounds__(kSpmvThreads)
 jacobi_kernel(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
-              const double2* __restrict__ vals, const double2* __restrict__ dinv,
-              const double2* __restrict__ b, const double2* __restrict__ xin, double2* __restrict__ xout,
-              double omega) {
+              const V* __restrict__ vals, const V* __restrict__ dinv,
+              const V* __restrict__ b, const V* __restrict__ xin, V* __restrict__ xout,
+              typename scalar_of<V>::type omega) {
     const int row = blockIdx.x * (kSpmvThreads / LANES) + threadIdx.x / LANES;
     const int lane = threadIdx.x % LANES;
     const bool valid = row < n;
     const int start = valid ? __ldg(indptr + row) : 0, end = valid ? __ldg(indptr + row + 1) : 0;
-    double2 acc = row_dot<LANES>(indices, vals, xin, start, end, lane);
+    V acc = row_dot<LANES, V, V>(indices, vals, xin, start, end, lane);
     if (valid && lane == 0) {
-        double2 r = csub(b[row], acc);
+        V r = csub(b[row], acc);
         xout[row] = cadd(xin[row], cscale(omega, cmul(dinv[row], r)));
     }
 }
 
-__global__ void jacobi_first_kernel(int n, const double2* __restrict__ dinv, const double2* __restrict__ b,
-                                    double2* __restrict__ xout, double omega) {
+template <typename V>
+__global__ void jacobi_first_kernel(int n, const V* __restrict__ dinv, const V* __restrict__ b,
+                                    V* __restrict__ xout, typename scalar_of<V>::type omega) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) xout[i] = cscale(omega, cmul(dinv[i], b[i]));
 }
@@ -128,26 +101,26 @@ __global__ void diag_pos_kernel(int n, const int* __restrict__ indptr, const int
 
 // ---- SELL-32: one thread per row, column-major inside a 32-row slice ----------
 // MODE 0: y = acc; 1: y = alpha*acc + beta*y0; 2: Jacobi xout = xin + omega*dinv*(b - acc)
-template <int UNROLL, int MINB, int MODE>
+template <int UNROLL, int MINB, int MODE, typename V = double2>
 __global__ void __launch_bounds__(256, MINB)
 sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, const int* __restrict__ cols,
-            const double2* __restrict__ vals, const int* __restrict__ row_perm, const double2* __restrict__ x,
-            double2* __restrict__ y, double2 alpha, double2 beta, const double2* __restrict__ y0,
-            const double2* __restrict__ dinv, const double2* __restrict__ b, double omega) {
+            const V* __restrict__ vals, const int* __restrict__ row_perm, const V* __restrict__ x,
+            V* __restrict__ y, V alpha, V beta, const V* __restrict__ y0,
+            const V* __restrict__ dinv, const V* __restrict__ b, typename scalar_of<V>::type omega) {
     const int slice = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (slice >= n_slices) return;
     const long long base = slice_ptr[slice];
     const int width = (int)((slice_ptr[slice + 1] - base) >> 5);
     const int* c = cols + base + lane;
-    const double2* v = vals + base + lane;
-    double2 acc[UNROLL];
+    const V* v = vals + base + lane;
+    V acc[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) acc[u] = make_double2(0.0, 0.0);
+    for (int u = 0; u < UNROLL; ++u) acc[u] = vzero<V>();
     int j = 0;
     for (; j + UNROLL <= width; j += UNROLL) {
         int cc[UNROLL];
-        double2 vv[UNROLL];
+        V vv[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) cc[u] = ld_stream(c + 32 * (j + u));
 #pragma unroll
@@ -157,7 +130,7 @@ sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, const 
     }
     for (; j < width; ++j) {
         const int c0 = ld_stream(c + 32 * j);
-        const double2 v0 = ld_stream(v + 32 * j);
+        const V v0 = ld_stream(v + 32 * j);
         cfma(acc[0], v0, __ldg(x + c0));
     }
 #pragma unroll
@@ -167,11 +140,11 @@ sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, const 
     const int row = row_perm[r];
     if (MODE == 0) y[row] = acc[0];
     else if (MODE == 1) {
-        double2 res = cmul(alpha, acc[0]);
+        V res = cmul(alpha, acc[0]);
         if (y0) res = cadd(res, cmul(beta, y0[row]));
         y[row] = res;
     } else {
-        const double2 res = csub(b[row], acc[0]);
+        const V res = csub(b[row], acc[0]);
         y[row] = cadd(x[row], cscale(omega, cmul(dinv[row], res)));
     }
 }
@@ -215,13 +188,14 @@ __global__ void sell_fill_kernel(int n, const int* __restrict__ indptr, const in
     }
 }
 
+template <typename V>
 __global__ void sell_gather_kernel(long long total, const int* __restrict__ src, const double2* __restrict__ csr_vals,
-                                   double2* __restrict__ out) {
+                                   V* __restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < total; i += stride) {
         const int s = ld_stream(src + i);
-        out[i] = (s >= 0) ? csr_vals[s] : make_double2(0.0, 0.0);
+        out[i] = (s >= 0) ? from_c128<V>(csr_vals[s]) : vzero<V>();
     }
 }
 
@@ -273,14 +247,14 @@ __global__ void lowrank_update_kernel(int nrows, const int* __restrict__ lrow, c
     y[row] = cadd(y[row], cmul(coef, acc));
 }
 
-template <typename VT>
-static int launch_spmv(int n, const int* indptr, const int* indices, const VT* vals, const double2* x, double2* y,
-                       double2 alpha, double2 beta, const double2* y0, int lanes, cudaStream_t st) {
+template <typename VT, typename V = double2>
+static int launch_spmv(int n, const int* indptr, const int* indices, const VT* vals, const V* x, V* y,
+                       V alpha, V beta, const V* y0, int lanes, cudaStream_t st) {
     if (n <= 0) return HX_OK;
 #define HX_SPMV_CASE(L)                                                                              \
     case L: {                                                                                        \
         const int rows_per_block = kSpmvThreads / L;                                                 \
-        spmv_csr_kernel<L, VT><<<ceil_div(n, rows_per_block), kSpmvThreads, 0, st>>>(n, indptr, indices, vals, x, y, \
+        spmv_csr_kernel<L, VT, V><<<ceil_div(n, rows_per_block), kSpmvThreads, 0, st>>>(n, indptr, indices, vals, x, y, \
                                                                                    alpha, beta, y0); \
         break;                                                                                       \
     }
@@ -307,7 +281,7 @@ extern "C" int hx_spmv_zz(int n, const int32_t* indptr, const int32_t* indices, 
     double2 alpha = alpha_h ? h2c(alpha_h) : make_double2(1.0, 0.0);
     double2 beta = beta_h ? h2c(beta_h) : make_double2(1.0, 0.0);
     if (lanes == 0) lanes = 8;
-    return launch_spmv<double2>(n, indptr, indices, (const double2*)vals, (const double2*)x, (double2*)y, alpha, beta,
+    return launch_spmv<double2, double2>(n, indptr, indices, (const double2*)vals, (const double2*)x, (double2*)y, alpha, beta,
                                 (const double2*)y0, lanes, (cudaStream_t)stream);
 }
 
@@ -319,19 +293,19 @@ extern "C" int hx_spmv_dz(int n, const int32_t* indptr, const int32_t* indices, 
     double2 alpha = alpha_h ? h2c(alpha_h) : make_double2(1.0, 0.0);
     double2 beta = beta_h ? h2c(beta_h) : make_double2(1.0, 0.0);
     if (lanes == 0) lanes = 8;
-    return launch_spmv<double>(n, indptr, indices, vals, (const double2*)x, (double2*)y, alpha, beta,
+    return launch_spmv<double, double2>(n, indptr, indices, vals, (const double2*)x, (double2*)y, alpha, beta,
                                (const double2*)y0, lanes, (cudaStream_t)stream);
 }
 
 namespace hx {
-template <int MODE>
-static int launch_sell(int variant, int n, int n_slices, const long long* sp, const int* cols, const double2* vals,
-                       const int* perm, const double2* x, double2* y, double2 alpha, double2 beta, const double2* y0,
-                       const double2* dinv, const double2* b, double omega, cudaStream_t st) {
+template <int MODE, typename V = double2>
+static int launch_sell(int variant, int n, int n_slices, const long long* sp, const int* cols, const V* vals,
+                       const int* perm, const V* x, V* y, V alpha, V beta, const V* y0,
+                       const V* dinv, const V* b, typename scalar_of<V>::type omega, cudaStream_t st) {
     const int warps = 8;
     const int grid = ceil_div(n_slices, warps);
 #define HX_SELL(U, MB)                                                                                          \
-    sell_kernel<U, MB, MODE><<<grid, warps * 32, 0, st>>>(n, n_slices, sp, cols, vals, perm, x, y, alpha, beta, y0, dinv, b, omega)
+    sell_kernel<U, MB, MODE, V><<<grid, warps * 32, 0, st>>>(n, n_slices, sp, cols, vals, perm, x, y, alpha, beta, y0, dinv, b, omega)
     switch (variant) {
         case 1: HX_SELL(4, 4); break;
         case 2: HX_SELL(4, 6); break;
@@ -351,9 +325,9 @@ extern "C" int hx_spmv_sell_zz(int n, int n_slices, const int64_t* slice_ptr, co
     if (n <= 0) return HX_OK;
     const double2 one = make_double2(1.0, 0.0);
     if (!alpha_h && !y0)
-        return launch_sell<0>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
+        return launch_sell<0, double2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
                               (const double2*)x, (double2*)y, one, one, nullptr, nullptr, nullptr, 0.0, (cudaStream_t)stream);
-    return launch_sell<1>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
+    return launch_sell<1, double2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
                           (const double2*)x, (double2*)y, alpha_h ? h2c(alpha_h) : one, beta_h ? h2c(beta_h) : one,
                           (const double2*)y0, nullptr, nullptr, 0.0, (cudaStream_t)stream);
 }
@@ -363,7 +337,7 @@ extern "C" int hx_jacobi_sell(int n, int n_slices, const int64_t* slice_ptr, con
                               double* xout, double omega, int variant, hx_stream_t stream) {
     if (n <= 0) return HX_OK;
     const double2 one = make_double2(1.0, 0.0);
-    return launch_sell<2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
+    return launch_sell<2, double2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const double2*)vals, row_perm,
                           (const double2*)xin, (double2*)xout, one, one, nullptr, (const double2*)dinv, (const double2*)b,
                           omega, (cudaStream_t)stream);
 }
@@ -389,8 +363,89 @@ extern "C" int hx_sell_gather(int64_t total, const int32_t* src, const double* c
     if (total <= 0) return HX_OK;
     long long blocks = ceil_div<long long>(total, 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    sell_gather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(total, src, (const double2*)csr_vals, (double2*)sell_vals);
+    sell_gather_kernel<double2><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(total, src, (const double2*)csr_vals, (double2*)sell_vals);
     return check_launch("sell_gather_kernel");
+}
+
+// ---- complex64 variants (mixed-precision AMG cycle) ------------------------------------------
+static inline float2 h2cf(const double* p) { return make_float2((float)p[0], (float)p[1]); }
+
+extern "C" int hx_sell_gather_c(int64_t total, const int32_t* src, const double* csr_vals, float* sell_vals,
+                                hx_stream_t stream) {
+    if (total <= 0) return HX_OK;
+    long long blocks = ceil_div<long long>(total, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    sell_gather_kernel<float2><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(total, src, (const double2*)csr_vals, (float2*)sell_vals);
+    return check_launch("sell_gather_kernel<float2>");
+}
+
+extern "C" int hx_spmv_cc(int n, const int32_t* indptr, const int32_t* indices, const float* vals, const float* x,
+                          float* y, const double* alpha_h, const double* beta_h, const float* y0, int lanes,
+                          hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    const float2 one = make_float2(1.f, 0.f);
+    if (lanes == 0) lanes = 8;
+    return launch_spmv<float2, float2>(n, indptr, indices, (const float2*)vals, (const float2*)x, (float2*)y,
+                                       alpha_h ? h2cf(alpha_h) : one, beta_h ? h2cf(beta_h) : one, (const float2*)y0, lanes,
+                                       (cudaStream_t)stream);
+}
+
+extern "C" int hx_spmv_sc(int n, const int32_t* indptr, const int32_t* indices, const float* vals, const float* x,
+                          float* y, const double* alpha_h, const double* beta_h, const float* y0, int lanes,
+                          hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    const float2 one = make_float2(1.f, 0.f);
+    if (lanes == 0) lanes = 8;
+    return launch_spmv<float, float2>(n, indptr, indices, vals, (const float2*)x, (float2*)y,
+                                      alpha_h ? h2cf(alpha_h) : one, beta_h ? h2cf(beta_h) : one, (const float2*)y0, lanes,
+                                      (cudaStream_t)stream);
+}
+
+extern "C" int hx_spmv_sell_cc(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols, const float* vals,
+                               const int32_t* row_perm, const float* x, float* y, const double* alpha_h,
+                               const double* beta_h, const float* y0, int variant, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    const float2 one = make_float2(1.f, 0.f);
+    if (!alpha_h && !y0)
+        return launch_sell<0, float2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const float2*)vals, row_perm,
+                                      (const float2*)x, (float2*)y, one, one, nullptr, nullptr, nullptr, 0.f, (cudaStream_t)stream);
+    return launch_sell<1, float2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const float2*)vals, row_perm,
+                                  (const float2*)x, (float2*)y, alpha_h ? h2cf(alpha_h) : one, beta_h ? h2cf(beta_h) : one,
+                                  (const float2*)y0, nullptr, nullptr, 0.f, (cudaStream_t)stream);
+}
+
+extern "C" int hx_jacobi_sell_c(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols, const float* vals,
+                                const int32_t* row_perm, const float* dinv, const float* b, const float* xin,
+                                float* xout, double omega, int variant, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    const float2 one = make_float2(1.f, 0.f);
+    return launch_sell<2, float2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const float2*)vals, row_perm,
+                                  (const float2*)xin, (float2*)xout, one, one, nullptr, (const float2*)dinv, (const float2*)b,
+                                  (float)omega, (cudaStream_t)stream);
+}
+
+extern "C" int hx_jacobi_sweep_c(int n, const int32_t* indptr, const int32_t* indices, const float* vals,
+                                 const float* dinv, const float* b, const float* xin, float* xout, double omega,
+                                 int lanes, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!xin) {
+        jacobi_first_kernel<float2><<<ceil_div(n, 256), 256, 0, st>>>(n, (const float2*)dinv, (const float2*)b, (float2*)xout, (float)omega);
+        return check_launch("jacobi_first_kernel<float2>");
+    }
+    if (lanes == 0) lanes = 8;
+#define HX_JACF_CASE(L)                                                                                   \
+    case L:                                                                                               \
+        jacobi_kernel<L, float2><<<ceil_div(n, kSpmvThreads / L), kSpmvThreads, 0, st>>>(                 \
+            n, indptr, indices, (const float2*)vals, (const float2*)dinv, (const float2*)b, (const float2*)xin, \
+            (float2*)xout, (float)omega);                                                                 \
+        break;
+    switch (lanes) {
+        HX_JACF_CASE(2) HX_JACF_CASE(4) HX_JACF_CASE(8) HX_JACF_CASE(16) HX_JACF_CASE(32)
+        default: return fail(HX_ERR_ARG, "jacobi: lanes must be 2,4,8,16,32%s%s");
+    }
+#undef HX_JACF_CASE
+    return check_launch("jacobi_kernel<float2>");
 }
 
 extern "C" int hx_combine_abc(int64_t nnz, const double* a, const double* b, const double* c, const double* ca_h,
@@ -426,13 +481,13 @@ extern "C" int hx_jacobi_sweep(int n, const int32_t* indptr, const int32_t* indi
     if (n <= 0) return HX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (!xin) {
-        jacobi_first_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, (const double2*)dinv, (const double2*)b, (double2*)xout, omega);
+        jacobi_first_kernel<double2><<<ceil_div(n, 256), 256, 0, st>>>(n, (const double2*)dinv, (const double2*)b, (double2*)xout, omega);
         return check_launch("jacobi_first_kernel");
     }
     if (lanes == 0) lanes = 8;
 #define HX_JAC_CASE(L)                                                                                    \
     case L:                                                                                               \
-        jacobi_kernel<L><<<ceil_div(n, kSpmvThreads / L), kSpmvThreads, 0, st>>>(                         \
+        jacobi_kernel<L, double2><<<ceil_div(n, kSpmvThreads / L), kSpmvThreads, 0, st>>>(                \
             n, indptr, indices, (const double2*)vals, (const double2*)dinv, (const double2*)b, (const double2*)xin, \
             (double2*)xout, omega);                                                                       \
         break;

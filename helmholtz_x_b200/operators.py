@@ -255,7 +255,7 @@ class ShiftedSolver:
     iteration the shift is the same for every iterate (only FTF(omega_k) changes), so the
     r extra solves are paid once per target instead of once per iterate."""
 
-    def __init__(self, ops: OperatorSet, terms, lowrank=(), rtol=1e-11, restart=40, maxiter=400, transposed=False):
+    def __init__(self, ops: OperatorSet, terms, lowrank=(), rtol=1e-11, restart=64, maxiter=512, transposed=False):
         import time
         if ops.part is not None:
             restart, maxiter = 80, 800          # the two-level Schwarz preconditioner needs more iterations

@@ -36,9 +36,11 @@ class SellPattern:
     def padding_ratio(self):
         return float(self.total) / max(self.nnz, 1)
 
-    def values_from_csr(self, csr_vals, out=None):
-        out = out if out is not None else self.be.empty(max(self.total, 1))
-        _lib.call("hx_sell_gather", self.total, self.src.data_ptr(), csr_vals.data_ptr(), out.data_ptr(), self.be.stream)
+    def values_from_csr(self, csr_vals, out=None, dtype=torch.complex128):
+        """SELL-ordered copy of complex128 CSR values (optionally down-converted to complex64)."""
+        out = out if out is not None else self.be.empty(max(self.total, 1), dtype=dtype)
+        name = "hx_sell_gather_c" if out.dtype == torch.complex64 else "hx_sell_gather"
+        _lib.call(name, self.total, self.src.data_ptr(), csr_vals.data_ptr(), out.data_ptr(), self.be.stream)
         return out
 
 
@@ -69,14 +71,16 @@ class SellMatrix:
         y0p = None
         if beta is not None:
             y0p = (y0 if y0 is not None else y).data_ptr()
-        _lib.call("hx_spmv_sell_zz", p.n, p.n_slices, p.slice_ptr.data_ptr(), p.cols.data_ptr(), self.vals.data_ptr(),
+        name = "hx_spmv_sell_cc" if self.vals.dtype == torch.complex64 else "hx_spmv_sell_zz"
+        _lib.call(name, p.n, p.n_slices, p.slice_ptr.data_ptr(), p.cols.data_ptr(), self.vals.data_ptr(),
                   p.row_perm.data_ptr(), x.data_ptr(), y.data_ptr(), _c2(alpha) if alpha is not None else None,
                   _c2(beta) if beta is not None else None, y0p, self.variant if variant is None else variant, self.be.stream)
         return y
 
     def jacobi(self, dinv, b, xin, xout, omega):
         p = self.p
-        _lib.call("hx_jacobi_sell", p.n, p.n_slices, p.slice_ptr.data_ptr(), p.cols.data_ptr(), self.vals.data_ptr(),
+        name = "hx_jacobi_sell_c" if self.vals.dtype == torch.complex64 else "hx_jacobi_sell"
+        _lib.call(name, p.n, p.n_slices, p.slice_ptr.data_ptr(), p.cols.data_ptr(), self.vals.data_ptr(),
                   p.row_perm.data_ptr(), dinv.data_ptr(), b.data_ptr(), xin.data_ptr(), xout.data_ptr(), float(omega),
                   self.variant, self.be.stream)
         return xout

@@ -77,6 +77,30 @@ int hx_sell_fill(int n, const int32_t* indptr, const int32_t* indices, const dou
 int hx_sell_gather(int64_t total, const int32_t* src, const double* csr_vals_c128, double* sell_vals_c128,
                    hx_stream_t stream);
 
+/* complex64 variants of the same kernels: the multigrid V-cycle used as GMRES
+ * preconditioner runs in single precision (matrix 12 B/nnz instead of 20), the outer
+ * GMRES / Krylov-Schur stay complex128.  Pointers are float (interleaved re,im). */
+int hx_spmv_cc(int n, const int32_t* indptr, const int32_t* indices, const float* vals_c64,
+               const float* x_c64, float* y_c64, const double* alpha_c128_h, const double* beta_c128_h,
+               const float* y0_c64, int lanes, hx_stream_t stream);
+int hx_spmv_sc(int n, const int32_t* indptr, const int32_t* indices, const float* vals_f32,
+               const float* x_c64, float* y_c64, const double* alpha_c128_h, const double* beta_c128_h,
+               const float* y0_c64, int lanes, hx_stream_t stream);
+int hx_spmv_sell_cc(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols,
+                    const float* vals_c64, const int32_t* row_perm, const float* x_c64, float* y_c64,
+                    const double* alpha_c128_h, const double* beta_c128_h, const float* y0_c64,
+                    int variant, hx_stream_t stream);
+int hx_jacobi_sell_c(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols,
+                     const float* vals_c64, const int32_t* row_perm, const float* dinv_c64,
+                     const float* b_c64, const float* xin_c64, float* xout_c64, double omega,
+                     int variant, hx_stream_t stream);
+int hx_jacobi_sweep_c(int n, const int32_t* indptr, const int32_t* indices, const float* vals_c64,
+                      const float* dinv_c64, const float* b_c64, const float* xin_c64, float* xout_c64,
+                      double omega, int lanes, hx_stream_t stream);
+/* SELL value refresh with down-conversion complex128 CSR values -> complex64 SELL values */
+int hx_sell_gather_c(int64_t total, const int32_t* src, const double* csr_vals_c128, float* sell_vals_c64,
+                     hx_stream_t stream);
+
 /* K8: P(sigma) = A + sigma B + sigma^2 C on the shared cell pattern, replacing the
  * MatAXPY chain of helmholtz_x/eigensolvers.py:174-176,240,309-315.  A, C real on
  * the full pattern; B complex on the same pattern or NULL.  out complex.

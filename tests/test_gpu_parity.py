@@ -339,6 +339,27 @@ def test_amg_vcycle_matches_host_double_and_gmres_converges():
     assert mats.ops.stats["inner_iterations"] <= 60, mats.ops.stats
 
 
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_amg_precision_modes_reach_full_accuracy(precision):
+    """The complex64 V-cycle is only a preconditioner: the complex128 GMRES must still reach 1e-11."""
+    from helmholtz_x_b200.operators import ShiftedSolver
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    mats.ops.amg_options = {"precision": precision}
+    s = case.target
+    solver = ShiftedSolver(mats.ops, {"A": 1.0, "B": s, "C": s ** 2}, rtol=1e-11)
+    assert solver.mg.single == (precision == "single")
+    rng = np.random.default_rng(8)
+    n = mats.ops.n
+    bvec = be().asarray(rng.standard_normal(n) + 1j * rng.standard_normal(n), dtype=torch.complex128)
+    x = be().zeros(n)
+    solver.solve(bvec, x)
+    P = solver.P.to_scipy()
+    res = np.linalg.norm(P @ x.cpu().numpy() - bvec.cpu().numpy()) / np.linalg.norm(bvec.cpu().numpy())
+    assert res < 5e-11, res
+    assert mats.ops.stats["inner_iterations"] <= 70, mats.ops.stats
+
+
 def test_passive_eps_matches_golden():
     """.../RijkeTube3D/Results/Passive/passive.log:30-33"""
     from helmholtz_x_b200.eigensolvers import eps_solver

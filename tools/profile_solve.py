@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--agg", type=int, default=8)
     ap.add_argument("--omega", type=float, default=2.0 / 3.0)
     ap.add_argument("--coarse-max", type=int, default=900)
+    ap.add_argument("--precision", default="single")
     a = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -36,7 +37,7 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         mats = AcousticMatrices(mesh, fem.MeshTags(mesh.facet_tags), {11: {"Robin": -0.875 - 0.2j}}, c, degree=1)
     s = bench.TARGET
-    mats.ops.amg_options = dict(nu=a.nu, agg_size=a.agg, omega=a.omega, coarse_max=a.coarse_max)
+    mats.ops.amg_options = dict(nu=a.nu, agg_size=a.agg, omega=a.omega, coarse_max=a.coarse_max, precision=a.precision)
     t0 = time.perf_counter()
     solver = ShiftedSolver(mats.ops, {"A": 1.0, "B": s, "C": s ** 2})
     torch.cuda.synchronize()
@@ -55,7 +56,12 @@ def main():
     dt = time.perf_counter() - t0
     torch.cuda.profiler.stop()
     its = mats.ops.stats["inner_iterations"] - it0
-    print(json.dumps({"nu": a.nu, "agg": a.agg, "omega": a.omega, "n": n, "setup_s": round(t_setup, 3), "solve_s": round(dt, 4), "iterations": its,
+    P = solver.P.to_scipy() if n <= 300000 else None
+    true_res = None
+    if P is not None:
+        xb, bb = x.cpu().numpy(), b.cpu().numpy()
+        true_res = float(np.linalg.norm(P @ xb - bb) / np.linalg.norm(bb))
+    print(json.dumps({"precision": a.precision, "true_residual": true_res, "nu": a.nu, "agg": a.agg, "omega": a.omega, "n": n, "setup_s": round(t_setup, 3), "solve_s": round(dt, 4), "iterations": its,
                       "ms_per_iteration": round(dt / its * 1e3, 4), "launches": be.launch_count(),
                       "amg_sizes": solver.mg.sizes, "operator_complexity": round(solver.mg.operator_complexity, 3),
                       "stats": mats.ops.stats}))
