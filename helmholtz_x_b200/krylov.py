@@ -38,9 +38,12 @@ class ArnoldiBasis:
         return host[:k].copy(), beta
 
 
-def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, basis=None, work=None):
+def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, basis=None, work=None, zbasis=None):
     """Right-preconditioned restarted GMRES: solves A x = b, x overwritten (start 0).
-    apply_A(v, out), precond(v, out).  Returns (iterations, relative residual)."""
+    apply_A(v, out), precond(v, out).  Returns (iterations, relative residual).
+    zbasis (restart x n): flexible GMRES -- the preconditioned vectors z_j = M^-1 v_j are kept
+    and x += Z y, so the Arnoldi relation A Z = V H holds exactly even when the preconditioner
+    is not an exact linear operator (the complex64 multigrid cycle)."""
     n = b.numel()
     if basis is None:
         basis = ArnoldiBasis(be, n, restart)
@@ -81,7 +84,10 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
         sn = np.zeros(m, complex)
         j_used = 0
         for j in range(m):
-            if precond is not None:
+            if precond is not None and zbasis is not None:
+                precond(V[j], zbasis[j])
+                apply_A(zbasis[j], w)
+            elif precond is not None:
                 precond(V[j], z)
                 apply_A(z, w)
             else:
@@ -114,13 +120,16 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
         y = np.linalg.solve(np.triu(H[:j_used, :j_used]), g[:j_used])
         # x += M^{-1} (V y)
         yd = be.asarray(-y, dtype=c128)
-        w.zero_()
-        be.multi_axpy(V, j_used, yd, w)
-        if precond is not None:
-            precond(w, z)
-            be.axpby(1.0, z, 1.0, x)
+        if precond is not None and zbasis is not None:
+            be.multi_axpy(zbasis, j_used, yd, x)          # x += Z y
         else:
-            be.axpby(1.0, w, 1.0, x)
+            w.zero_()
+            be.multi_axpy(V, j_used, yd, w)
+            if precond is not None:
+                precond(w, z)
+                be.axpby(1.0, z, 1.0, x)
+            else:
+                be.axpby(1.0, w, 1.0, x)
         if rel <= rtol:
             break
     return total, rel

@@ -292,7 +292,8 @@ class ShiftedSolver:
                 ops.coarse().set_shift(t)
             st = {"key": key, "P_values": P_values, "P": P, "Pop": Pop, "wood": {},
                   "basis": krylov.ArnoldiBasis(be, ops.n, restart), "work": be.zeros(ops.n),
-                  "xc": be.zeros(ops.n), "r": be.zeros(ops.n)}
+                  "xc": be.zeros(ops.n), "r": be.zeros(ops.n),
+                  "zbasis": be.zeros(restart, ops.n) if getattr(mg, "single", False) else None}
             ops._shift_state = st
             ops.stats["shifts"] += 1
             ops.stats["t_shift"] += time.perf_counter() - t_shift0
@@ -324,7 +325,8 @@ class ShiftedSolver:
         import time
         t0 = time.perf_counter()
         its, rel = krylov.gmres(self.be, lambda v, o: self.be.spmv(self.Pop, v, o), b, x, precond=self._precond,
-                                rtol=self.rtol, restart=self.restart, maxiter=self.maxiter, basis=self.basis, work=self.work)
+                                rtol=self.rtol, restart=self.restart, maxiter=self.maxiter, basis=self.basis, work=self.work,
+                                zbasis=self.st["zbasis"])
         self.ops.stats["inner_solves"] += 1
         self.ops.stats["inner_iterations"] += its
         self.ops.stats["t_inner"] += time.perf_counter() - t0
