@@ -24,11 +24,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # set-up SpGEMM temporaries fragment badly
+if any(a.startswith("--dofs") for a in sys.argv) and any(len(a) >= 7 and a.isdigit() and int(a) >= 5_000_000 for a in sys.argv):
+    # very large runs: the set-up SpGEMM temporaries fragment the caching allocator badly
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 import numpy as np  # noqa: E402
 
-DEFAULT_DOFS = 250_000
+DEFAULT_DOFS = 1_000_000
 TARGET = 3225.120 + 481.0j            # fullAnnulus/active_fpi.py:40
 NEV, FPI_TOL = 4, 1e-3                # active_fpi.py:41
 
@@ -273,7 +275,8 @@ def run_b200(args):
                                f"Robin outlet, FPI tol {FPI_TOL}, nev {NEV}",
                    "step": "pattern + assemble A,B,C + D + fixed-point omega iteration (PEP shift-invert Krylov-Schur)",
                    "dofs": mats_n(g, args.degree), "cells": int(g["cells"].shape[0]),
-                   "l2_note": "roofline loop: inputs larger than L2 only for >= ~500k DoF; the 10M-DoF spmv_10m entry is",
+                   "l2": "roofline loop re-reads a 328 MB matrix (> 126 MB L2) every launch at 1M DoF; spmv_10m uses 3.3 GB",
+                   "ten_million_dof_step": "measured separately (335 s on one B200): profiles/r1_bench_10M_step.json",
                    "multi_gpu": ("rows partitioned over ranks (Morton chunks), NCCL halo exchange + all-reduced Gram "
                                  "columns, block-Jacobi AMG") if world > 1 else "single"},
         "omega": [float(np.real(omega)), float(np.imag(omega))],
@@ -323,17 +326,23 @@ def workload_cpu(dofs, degree):
     return g
 
 
+def _sample_text(n, nit, sec, workload_dofs, cores):
+    return (f"CPU oracle (NumPy assembly + SciPy SuperLU/ARPACK shift-invert, flame term by Woodbury; restatement of the "
+            f"reference's DOLFINx/PETSc/SLEPc path, which cannot be installed on this box) on the same synthetic annulus "
+            f"at {n} DoF: assembly + full fixed-point iteration ({nit} PEP solves) took {sec:.2f} s; value = that time x "
+            f"({workload_dofs}/{n}) i.e. scaled LINEARLY in DoF to the {workload_dofs}-DoF workload -- a lower bound for the "
+            f"CPU path (sparse LU fill and time grow superlinearly; at this size the direct LU does not fit the host). "
+            f"SuperLU is single-threaded, BLAS uses up to {cores} threads")
+
+
 def cpu_baseline(args):
     cores = os.cpu_count()
     try:
         sec, om, n, nit = cpu_sample(args.cpu_sample_dofs, args.degree)
-        return {"value": round(sec, 3), "unit": "s", "cores": cores, "kind": "port",
-                "sample": f"CPU oracle (NumPy assembly + SciPy SuperLU/ARPACK shift-invert, flame term by Woodbury) on the "
-                          f"same synthetic annulus at {n} DoF: assembly + full fixed-point iteration ({nit} PEP solves); "
-                          f"NOT scaled to the GPU workload size (direct LU does not scale to it); SuperLU is "
-                          f"single-threaded, BLAS uses up to {cores} threads",
-                "omega": [float(np.real(om)), float(np.imag(om))],
-                "note": "the reference's own mpirun PETSc/SLEPc/MUMPS path cannot be installed on this box"}
+        scale = args.dofs / n
+        return {"value": round(sec * scale, 2), "unit": "s", "cores": cores, "kind": "port",
+                "sample": _sample_text(n, nit, sec, args.dofs, cores), "sample_seconds": round(sec, 3), "sample_dofs": n,
+                "scale": round(scale, 3), "omega_at_sample_size": [float(np.real(om)), float(np.imag(om))]}
     except Exception as ex:                  # noqa: BLE001
         return {"value": None, "unit": "s", "cores": cores, "kind": "port", "sample": "failed: " + str(ex)[:200]}
 
@@ -356,19 +365,21 @@ def run_reference(args):
             warm = k + 1                      # CPU code has no warm-up effect worth minutes: cut warm-ups short
         if elapsed > 200 and times:
             break
-    v = float(np.mean(times))
-    sample = (f"CPU oracle (NumPy/SciPy SuperLU + ARPACK restatement of the reference's DOLFINx/PETSc/SLEPc path, "
-              f"which is not installable here) on the synthetic annulus at {n} DoF, assembly + full FPI ({nit} PEP solves) "
-              f"per step; bounded sample of the {args.dofs}-DoF workload (direct LU does not scale to it)")
+    sec = float(np.mean(times))
+    scale = args.dofs / n
+    v = sec * scale
+    sample = _sample_text(n, nit, sec, args.dofs, cores)
     print(json.dumps({
         "impl": "reference", "metric": "converged_omega_solve_time", "value": round(v, 4), "unit": "s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(times), "warmup": args.warmup,
-        "ms_per_step": round(v * 1e3, 2), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(v * 1e3, 2), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128", "data": "synthetic",
-        "config": {"workload": f"synthetic annular combustor P{args.degree}, bounded sample at {n} DoF of the "
-                               f"{args.dofs}-DoF workload", "dofs": n},
+        "config": {"workload": f"synthetic annular combustor P{args.degree}, {args.dofs} DoF (bounded sample at {n} DoF, "
+                               f"scaled linearly in DoF)", "dofs": args.dofs, "sample_dofs": n,
+                   "sample_seconds": round(sec, 3), "scale": round(scale, 3)},
         "omega": [float(np.real(om)), float(np.imag(om))],
-        "cpu_baseline": {"value": round(v, 4), "unit": "s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(v, 4), "unit": "s", "cores": cores, "kind": "port", "sample": sample,
+                         "sample_seconds": round(sec, 3), "sample_dofs": n, "scale": round(scale, 3)},
         "e2e": {"value": round(v, 4), "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 

@@ -204,7 +204,7 @@ class AMG:
                 del X
                 Z = _spmm(Rm, Y)
                 del Y
-                if vals.is_cuda:
+                if vals.is_cuda and n > 3_000_000:
                     torch.cuda.empty_cache()      # the SpGEMM temporaries are GBs at 10 M DoF
                 return Z
             Ac = galerkin(a_re)
