@@ -134,6 +134,7 @@ class AMG:
         precision="single": the V-cycle (smoother, residual, transfers) runs in complex64 --
         it is only a preconditioner; GMRES and everything outside stay complex128."""
         self.be, self.nu, self.omega = be, nu, omega
+        self.native_min_rows = 20000
         self.single = precision == "single" and getattr(be, "supports_mixed", False)
         self.wdtype = torch.complex64 if self.single else c128
         self.sell_min_rows = sell_min_rows if getattr(be, "supports_sell", False) else None
@@ -164,6 +165,16 @@ class AMG:
             nc = int(agg.max().item()) + 1
             cnt = torch.bincount(agg, minlength=nc).to(f64)
             tval = 1.0 / torch.sqrt(cnt[agg])
+            if getattr(be, "supports_spgemm", False) and n >= self.native_min_rows:
+                from .spgemm import Overflow
+                try:
+                    L.P, L.R, pat, a_re, c_re, b_cx = self._coarsen_native(be, pat, a_re, c_re, b_cx, agg, nc, tval, tau)
+                    csum = torch.zeros(nc, 3, dtype=f64, device=dev)
+                    csum.index_add_(0, agg, coords)
+                    coords = csum / cnt.view(-1, 1)
+                    continue
+                except Overflow:
+                    pass          # a product row exceeds the kernel's shared-memory budget: library path below
             T = torch.sparse_coo_tensor(torch.stack([torch.arange(n, device=dev), agg]), tval, size=(n, nc)).coalesce()
             kval = -a_re + tau * c_re
             K = _to_coo(pat, kval)
@@ -247,6 +258,49 @@ class AMG:
         last.b64 = be.zeros(last.n)
         last.x64 = be.zeros(last.n)
         self.coarse_inv = None
+
+    def _coarsen_native(self, be, pat, a_re, c_re, b_cx, agg, nc, tval, tau):
+        """One coarsening step with the library's own SpGEMM kernels (hx_spgemm_*): P = (I - w D^-1 K) T,
+        R = P^T, and the Galerkin products on ONE symbolic pattern shared by A, C, Re B, Im B."""
+        from . import spgemm
+        n, dev = pat.n_rows, a_re.device
+        self.native_levels = getattr(self, "native_levels", 0) + 1
+        kval = -a_re + tau * c_re
+        rows = _rows_of(pat.indptr, pat.nnz)
+        d = _diag(pat.with_values(kval))
+        S = pat.with_values((kval / d[rows]).contiguous())
+        # same (deliberately low) spectral-radius estimate as the library path: 12 power steps from a smooth vector
+        v = (torch.ones(n, dtype=f64, device=dev) + 0.1 * torch.sin(torch.arange(n, device=dev, dtype=f64))).to(c128)
+        w = torch.zeros_like(v)
+        rho = 1.0
+        for _ in range(12):
+            be.spmv(S, v, w)
+            rho = float(torch.linalg.norm(w))
+            v, w = w / rho, v
+        self.rhos = getattr(self, "rhos", []) + [round(rho, 4)]
+        T = CsrMatrix(n, nc, torch.arange(n + 1, device=dev, dtype=torch.int32), agg.to(torch.int32).contiguous(), tval.contiguous())
+        ST = spgemm.multiply(be, S, T)
+        pvals = (-(4.0 / (3.0 * rho))) * ST.values
+        keys = _rows_of(ST.indptr, ST.nnz) * nc + ST.indices.long()                 # sorted (CSR order)
+        pos = torch.searchsorted(keys, torch.arange(n, device=dev) * nc + agg)
+        pvals[pos] += tval                                                          # + T (its entry lies in the pattern of S*T)
+        P = ST.with_values(pvals.contiguous())
+        R = spgemm.transpose(P)
+        yp = spgemm.symbolic(be, pat, P)
+        Ypat = CsrMatrix(n, nc, yp[0], yp[1], None)
+        zp = spgemm.symbolic(be, R, Ypat)
+        ybuf = be.empty(max(int(yp[1].numel()), 1), dtype=f64)
+
+        def galerkin(vals):
+            yv = spgemm.numeric(be, pat.with_values(vals.contiguous()), P, yp[0], yp[1], out=ybuf)
+            return spgemm.numeric(be, R, CsrMatrix(n, nc, yp[0], yp[1], yv), zp[0], zp[1]).clone()
+        a_c = galerkin(a_re)
+        c_c = galerkin(c_re)
+        b_c = None
+        if b_cx is not None:
+            b_c = torch.complex(galerkin(b_cx.real), galerkin(b_cx.imag))
+        pat_c = CsrMatrix(nc, nc, zp[0], zp[1], torch.zeros(int(zp[1].numel()), dtype=f64, device=dev))
+        return P, R, pat_c, a_c, c_c, b_c
 
     @property
     def sizes(self):

@@ -86,6 +86,7 @@ class CudaBackend:
     name = "cuda"
     supports_sell = True
     supports_mixed = True        # complex64 kernels for the multigrid cycle
+    supports_spgemm = True       # hx_spgemm_* for the multigrid set-up
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():

@@ -164,6 +164,16 @@ int hx_diag_positions(int n, const int32_t* indptr, const int32_t* indices, int3
 int hx_dense_inverse(int n, double* a_c128_colmajor, int32_t* info_dev, hx_stream_t stream);
 int hx_dense_gemv(int n, const double* a_c128_colmajor, const double* x_c128, double* y_c128, hx_stream_t stream);
 
+/* multigrid set-up: C = A * B on CSR (real double), one warp per row.  symbolic: distinct
+ * column count per row (write_cols=0; -1 = more than 2048 columns, caller falls back) or the
+ * sorted columns (write_cols=1); numeric: deterministic accumulation into a given pattern. */
+int hx_spgemm_symbolic(int m, const int32_t* a_ptr, const int32_t* a_idx, const int32_t* b_ptr,
+                       const int32_t* b_idx, int32_t* row_nnz, const int32_t* c_ptr, int32_t* c_idx,
+                       int write_cols, hx_stream_t stream);
+int hx_spgemm_numeric(int m, const int32_t* a_ptr, const int32_t* a_idx, const double* a_val,
+                      const int32_t* b_ptr, const int32_t* b_idx, const double* b_val,
+                      const int32_t* c_ptr, const int32_t* c_idx, double* c_val, hx_stream_t stream);
+
 /* ------------------------------------------------------------------ K4
  * DOLFINx SparsityPattern + MatCreateAIJ (acoustic_matrices.py:102): CSR pattern
  * from the cell dofmap (n_cells x nd, int32).  Three steps so the caller can

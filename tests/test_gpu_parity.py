@@ -291,6 +291,46 @@ def test_dense_inverse_and_gemv():
         assert relmax(y.cpu().numpy(), np.linalg.solve(A, x)) < 1e-9
 
 
+def test_spgemm_kernels_match_scipy_and_are_deterministic():
+    """hx_spgemm_symbolic / hx_spgemm_numeric (multigrid set-up) against SciPy: pattern bit-exact."""
+    import scipy.sparse as sp
+    from helmholtz_x_b200 import spgemm
+    from helmholtz_x_b200.backend import CsrMatrix
+    b = be()
+    rng = np.random.default_rng(5)
+
+    def dev(Ms):
+        Ms = Ms.tocsr(); Ms.sort_indices()
+        return CsrMatrix(Ms.shape[0], Ms.shape[1], b.asarray(Ms.indptr.astype(np.int32)), b.asarray(Ms.indices.astype(np.int32)),
+                         b.asarray(Ms.data.astype(np.float64)))
+    case = cases.annulus()
+    ops = cases.oracle_operators(case)
+    A = ops.A.real.tocsr()
+    n = A.shape[0]
+    agg = np.arange(n) // 7
+    T = sp.csr_matrix((rng.standard_normal(n), (np.arange(n), agg)), shape=(n, agg.max() + 1))
+    P = (A @ T).tocsr()                                       # a realistic, wider right factor
+    for X, Y in ((A, T), (A, P), (P.T.tocsr(), (A @ P).tocsr())):
+        C1 = spgemm.multiply(b, dev(X), dev(Y))
+        C2 = spgemm.multiply(b, dev(X), dev(Y))
+        assert torch.equal(C1.values, C2.values)
+        ref = (abs(X) @ abs(Y)).tocsr(); ref.sort_indices()
+        assert np.array_equal(C1.indptr.cpu().numpy(), ref.indptr)
+        assert np.array_equal(C1.indices.cpu().numpy(), ref.indices)
+        val = (X @ Y).tocsr()
+        got = sp.csr_matrix((C1.values.cpu().numpy(), C1.indices.cpu().numpy(), C1.indptr.cpu().numpy()), shape=val.shape)
+        assert abs(got - val).max() < 1e-12 * abs(val).max()
+    Rt = spgemm.transpose(dev(P))
+    assert abs(Rt.to_scipy() - P.T).max() == 0.0
+    # empty rows and an overflowing row (> 2048 distinct columns) are handled
+    E = sp.csr_matrix((3, n))
+    assert spgemm.multiply(b, dev(E), dev(A)).nnz == 0
+    wide = sp.csr_matrix((np.ones(3000), (np.zeros(3000, int), np.arange(3000))), shape=(1, n))
+    D = sp.identity(n, format="csr")
+    with pytest.raises(spgemm.Overflow):
+        spgemm.multiply(b, dev(wide), dev(D))
+
+
 def test_ilu0_level_scheduled_matches_host_ilu0():
     from helmholtz_x_b200.ilu import ILU0
     case = cases.rijke3d()

@@ -140,3 +140,56 @@ def test_two_sided_left_vectors(rijke):
     assert np.linalg.norm(Ls @ x - lam * (Cs @ x)) < 1e-7 * np.linalg.norm(Ls @ x)
     r = y.conj() @ Ls - lam * (y.conj() @ Cs)
     assert np.linalg.norm(r) < 1e-7 * np.linalg.norm(y.conj() @ Ls)
+
+
+def test_native_spgemm_coarsening_path_matches_library_path(rijke, monkeypatch):
+    """amg._coarsen_native (hx_spgemm_* kernels on the GPU) against the torch.sparse path, with the
+    kernels replaced by SciPy stand-ins: checks the prolongator assembly, transpose and the shared
+    Galerkin pattern logic on CPU."""
+    import scipy.sparse as sp
+    from helmholtz_x_b200 import amg, spgemm
+    from helmholtz_x_b200.backend import CsrMatrix
+
+    def to_sp(M, vals=None):
+        v = M.values if vals is None else vals
+        v = np.ones(M.indices.numel()) if v is None else v.numpy()
+        return sp.csr_matrix((v, M.indices.numpy(), M.indptr.numpy()), shape=M.shape)
+
+    def fake_symbolic(be, A, B):
+        C = (abs(to_sp(A, torch.ones(A.indices.numel(), dtype=torch.float64)))
+             @ abs(to_sp(B, torch.ones(B.indices.numel(), dtype=torch.float64)))).tocsr()
+        C.sort_indices()
+        return torch.from_numpy(C.indptr.astype(np.int32)), torch.from_numpy(C.indices.astype(np.int32))
+
+    def fake_numeric(be, A, B, indptr, indices, out=None):
+        C = (to_sp(A) @ to_sp(B)).tocsr()
+        n = len(indptr) - 1
+        Pm = sp.csr_matrix((np.arange(1, len(indices) + 1), indices.numpy(), indptr.numpy()), shape=(n, B.n_cols))
+        coo = C.tocoo()
+        vals = np.zeros(len(indices))
+        vals[np.asarray(Pm[coo.row, coo.col]).ravel() - 1] = coo.data
+        return torch.from_numpy(vals)
+
+    monkeypatch.setattr(spgemm, "symbolic", fake_symbolic)
+    monkeypatch.setattr(spgemm, "numeric", fake_numeric)
+    _, hops = rijke
+    be = hops.ops.be
+    pat = hops.V.matrix
+    A, C = pat(hops.ops.base["A"]), pat(hops.ops.base["C"])
+    ref = amg.AMG(be, A, C, None, hops.V.dof_coords, agg_size=8)
+
+    class NativeAMG(amg.AMG):          # force the native path on this small problem
+        native_min_rows = property(lambda self: 0, lambda self, v: None)
+    be.supports_spgemm = True
+    nat = NativeAMG(be, A, C, None, hops.V.dof_coords, agg_size=8)
+    be.supports_spgemm = False
+    assert nat.sizes == ref.sizes and nat.native_levels == len(nat.sizes) - 1
+    for Ln, Lr in zip(nat.levels[:-1], ref.levels[:-1]):
+        assert abs(to_sp(Ln.P) - to_sp(Lr.P)).max() < 1e-12
+        assert abs(to_sp(Ln.R) - to_sp(Lr.R)).max() < 1e-12
+    a1n = to_sp(nat.levels[1].pattern, nat.levels[1].a)
+    a1r = to_sp(ref.levels[1].pattern, ref.levels[1].a)
+    assert abs(a1n - a1r).max() < 1e-9 * abs(a1r).max()
+    c1n = to_sp(nat.levels[1].pattern, nat.levels[1].c)
+    c1r = to_sp(ref.levels[1].pattern, ref.levels[1].c)
+    assert abs(c1n - c1r).max() < 1e-9 * abs(c1r).max()
