@@ -236,9 +236,12 @@ def run_b200(args):
     ms, nbytes = spmv_roofline(be, sell)
     ms_csr, _ = spmv_roofline(be, csr)
     achieved = nbytes / (ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "sell_kernel<2,8,0> (hx_spmv_sell_zz, the solver's fine-level SpMV format)",
+    roof = {"bound": "hbm", "kernel": "sell_kernel<4,4,0,double2> (hx_spmv_sell_zz, the solver's fine-level SpMV format)",
             "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None, "bytes_per_launch": nbytes,
+            "frac": round(achieved / peak, 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this matrix, one `ncu --set full`
+            # capture (profiles/r1_prof_sell_1M_raw_v2.csv); only valid for the default workload
+            "traffic": 318.4e6 if (csr.n_rows == 998400 and world == 1) else None, "bytes_per_launch": nbytes,
             "ms_per_launch": round(ms, 5), "n": csr.n_rows, "nnz": csr.nnz, "model": "20*nnz + 36*n bytes (SURVEY 8d)",
             "csr_vector_gbs": round(nbytes / (ms_csr * 1e-3) / 1e9, 1)}
     big = None

@@ -312,7 +312,7 @@ static int launch_sell(int variant, int n, int n_slices, const long long* sp, co
         case 3: HX_SELL(2, 8); break;
         case 4: HX_SELL(4, 8); break;
         case 5: HX_SELL(8, 4); break;
-        case 0: default: HX_SELL(2, 8); break;   // best on B200: 6.0 TB/s at 10M DoF (profiles/r1_spmv_bench_10m_v2.json)
+        case 0: default: HX_SELL(4, 4); break;   // best on B200: 6.0 TB/s at 1M and 10M DoF (profiles/README.md)
     }
 #undef HX_SELL
     return check_launch("sell_kernel");

@@ -84,3 +84,45 @@ def grid_for_dofs(n_dofs, degree=1):
     n_theta = max(16, int(round(1.1 / h / 16)) * 16)
     n_z = max(4, int(round(n_nodes / (n_r * n_theta))))
     return n_r, n_theta, n_z
+
+
+def slab_grid(nx, ny, L, h, thickness=None):
+    """The reference's 2-D rectangle [0,L]x[0,h] (dolfinx_utils.RectangleSetup, used by
+    numerical_examples/manufacturedSolution/manufacturedHelmholtz.py:12-15) as a one-cell-thick
+    extruded slab of Kuhn tetrahedra: modes that do not vary in z are exactly those of the 2-D
+    problem, so the P1-tetrahedron path covers BASELINE config 2.  Facet tags as in
+    RectangleSetup: 1 left (x=0), 2 right (x=L), 3 bottom (y=0), 4 top (y=h)."""
+    t = thickness if thickness is not None else min(L / nx, h / ny)
+    xs, ys, zs = np.linspace(0, L, nx + 1), np.linspace(0, h, ny + 1), np.array([0.0, t])
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    x = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+    def nid(i, j, k):
+        return (k * (ny + 1) + j) * (nx + 1) + i
+    I, J = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    I, J = I.ravel(), J.ravel()
+    K = np.zeros_like(I)
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        off = [0, 0, 0]
+        verts = [nid(I, J, K)]
+        for ax in perm:
+            off[ax] = 1
+            verts.append(nid(I + off[0], J + off[1], K + off[2]))
+        tets.append(np.stack(verts, axis=1))
+    cells = np.stack(tets, axis=1).reshape(-1, 4)
+    facets, tags = [], []
+
+    def quad(a, b, c, d, tag):       # a-b-d-c around the quad, split along the Kuhn diagonal a-d
+        facets.extend([np.stack([a, b, d], 1), np.stack([a, c, d], 1)])
+        tags.extend([np.full(len(a), tag), np.full(len(a), tag)])
+    jj = np.arange(ny)
+    ii = np.arange(nx)
+    z0, z1 = np.zeros_like(jj), np.ones_like(jj)
+    quad(nid(0 * jj, jj, z0), nid(0 * jj, jj + 1, z0), nid(0 * jj, jj, z1), nid(0 * jj, jj + 1, z1), 1)
+    quad(nid(0 * jj + nx, jj, z0), nid(0 * jj + nx, jj + 1, z0), nid(0 * jj + nx, jj, z1), nid(0 * jj + nx, jj + 1, z1), 2)
+    z0, z1 = np.zeros_like(ii), np.ones_like(ii)
+    quad(nid(ii, 0 * ii, z0), nid(ii + 1, 0 * ii, z0), nid(ii, 0 * ii, z1), nid(ii + 1, 0 * ii, z1), 3)
+    quad(nid(ii, 0 * ii + ny, z0), nid(ii + 1, 0 * ii + ny, z0), nid(ii, 0 * ii + ny, z1), nid(ii + 1, 0 * ii + ny, z1), 4)
+    return dict(x=x, cells=cells.astype(np.int32), cell_tags=np.zeros(len(cells), np.int32),
+                facets=np.concatenate(facets).astype(np.int32), facet_tags=np.concatenate(tags).astype(np.int32))

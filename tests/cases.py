@@ -136,3 +136,31 @@ def oracle_flame(case):
                                     case.degree, gamma=case.gamma)
     return ox.pointwise_flame(case.mesh, case.x_r, case.h, case.rho_u, case.q_0, case.u_b, ftf, case.degree,
                               gamma=case.gamma)
+
+
+def manufactured():
+    """BASELINE config 2: numerical_examples/manufacturedSolution/manufacturedHelmholtz.py:12-33 --
+    rectangle 0.4 x 0.1, 160 x 40, c0 = 450, Robin (impedance Z) on the top wall (tag 4), passive PEP.
+    The reference's mesh is 2-D; here it is the one-cell-thick extruded slab of Kuhn tetrahedra
+    (helmholtz_x_b200.synthetic.slab_grid): z-invariant modes coincide with the 2-D problem."""
+    from helmholtz_x_b200 import synthetic
+    if "manufactured" not in _mesh_cache:
+        g = synthetic.slab_grid(160, 40, 0.4, 0.1)
+        _mesh_cache["manufactured"] = ox.Mesh(g["x"], g["cells"].astype(np.int64), g["cell_tags"],
+                                              g["facets"].astype(np.int64), g["facet_tags"])
+    m = _mesh_cache["manufactured"]
+    return Case(mesh=m, degree=1, bcs=None, c=np.full(m.n_nodes, 450.0), parameter_is_temperature=False, c_is_dg0=False,
+                nev=2)
+
+
+def manufactured_bcs(Z):
+    return {4: {"Robin": (Z - 1) / (Z + 1)}}
+
+
+def manufactured_goldens():
+    g = golden_values()["manufactured_analytic"]
+    out = []
+    for zk, fk in (("Z_imag", "f_imagZ"), ("Z_real", "f_realZ")):
+        for z, f in zip(g[zk], g[fk]):
+            out.append((cplx(z), cplx(f)))
+    return out

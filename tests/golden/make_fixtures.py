@@ -106,6 +106,14 @@ def main():
     g["flamedduct_active_fpi"] = dict(source=D + ":28-56", omegas=omegas_from_log(D, 21, 56))
     B = "AnnularCombustor/Micca/bloch/Results/Passive/passive.log"
     g["bloch_passive"] = dict(source=B + ":27-31", omegas=[2931.177998, 4633.352640, 11107.674019])
+    # config 2: manufactured 2-D duct, analytic dispersion roots written by the reference's MATLAB script
+    rows = [ln.split() for ln in open(REF + "manufacturedSolution/matlab_data/analytical.txt").read().splitlines() if ln.strip()]
+    sel = [0, 60, 140, 260, 340, 399]
+    zb = np.linspace(-10j, 10j, 400); za = np.linspace(-10, 10, 400)
+    g["manufactured_analytic"] = dict(
+        source="manufacturedSolution/matlab_data/analytical.txt (rows %s; columns Re f_b, Im f_b, Re f_a, Im f_a in Hz, 1 decimal)" % sel,
+        Z_imag=[[0.0, float(zb[i].imag)] for i in sel], f_imagZ=[[float(rows[i][0]), float(rows[i][1])] for i in sel],
+        Z_real=[[float(za[i]), 0.0] for i in sel], f_realZ=[[float(rows[i][2]), float(rows[i][3])] for i in sel])
     with open(os.path.join(HERE, "golden_values.json"), "w") as fh:
         json.dump(g, fh, indent=1)
     print("golden values", {k: len(v.get("omegas", [])) for k, v in g.items()})

@@ -127,3 +127,15 @@ def test_p2_space_and_operators_are_consistent():
     assert np.abs(ops.A @ one).max() < 1e-6 * np.abs(ops.A.data).max()
     vol, _ = ox.geometry(case.mesh)
     assert abs(one @ (ops.C @ one) - vol.sum()) < 1e-12
+
+
+def test_manufactured_config2_against_analytic_goldens():
+    """BASELINE config 2: the reference compares its FEM result with the MATLAB dispersion roots in
+    manufacturedSolution/matlab_data/analytical.txt (1 decimal, Hz); same check for the oracle."""
+    case = cases.manufactured()
+    for Z, f_gold in cases.manufactured_goldens()[::3]:
+        case["bcs"] = cases.manufactured_bcs(Z)
+        ops = cases.oracle_operators(case)
+        E = ox.pep_solve(ops.A, ops.B, ops.C, 2 * np.pi * f_gold.real, 2)
+        f = E.eigenvalues[0] / (2 * np.pi)
+        assert abs(f - f_gold) < 0.06 + 3e-5 * abs(f_gold), (Z, f, f_gold)
