@@ -206,9 +206,23 @@ def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, 
     its = 0
     n_apply = 0
     Vnew = None
+    def ritz(mm):
+        """Ordered Schur form of the current mm x mm projection and the Ritz residual estimates."""
+        T, Z = sla.schur(H[:mm, :mm], output="complex")
+        T, Z = _reorder_schur(T, Z, np.abs)
+        bt = H[mm, :mm] @ Z
+        Y = _triu_eigvecs(T)
+        theta = np.diag(T).copy()
+        res = np.abs(bt @ Y)
+        nconv = 0
+        while nconv < mm and res[nconv] <= tol * abs(theta[nconv]):
+            nconv += 1
+        return T, Z, bt, Y, theta, res, nconv
+
     while True:
         its += 1
         mm = m
+        early = None
         for j in range(k, m):
             apply_op(V[j], w)
             n_apply += 1
@@ -218,16 +232,15 @@ def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, 
             if hb <= 1e-14 * max(np.abs(h).max(), 1e-300):
                 mm = j + 1        # invariant subspace found
                 break
-        T, Z = sla.schur(H[:mm, :mm], output="complex")
-        T, Z = _reorder_schur(T, Z, np.abs)
-        bt = H[mm, :mm] @ Z if mm == m or True else None
-        bt = H[mm, :mm] @ Z
-        Y = _triu_eigvecs(T)
-        theta = np.diag(T).copy()
-        res = np.abs(bt @ Y)
-        nconv = 0
-        while nconv < mm and res[nconv] <= tol * abs(theta[nconv]):
-            nconv += 1
+            # early exit: with a good start vector (warm-started fixed-point iterates) the wanted
+            # pairs converge long before the basis is full -- test the small projection as we go
+            if j + 1 >= max(nev + 2, k + 2) and j + 1 < m:
+                early = ritz(j + 1)
+                if early[-1] >= nev:
+                    mm = j + 1
+                    break
+                early = None
+        T, Z, bt, Y, theta, res, nconv = early if early is not None else ritz(mm)
         if nconv >= nev or its >= maxit or mm < m:
             break
         keep = min(max(nconv + (m - nconv) // 2, nev), m - 1)

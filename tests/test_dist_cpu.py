@@ -46,10 +46,48 @@ def _sub_values(part, Mglob, pattern):
     P = sp.csr_matrix((np.arange(1, len(pattern[1]) + 1), pattern[1].numpy(), pattern[0].numpy()), shape=(n, n))
     out = np.zeros(len(pattern[1]), dtype=sub.dtype)
     coo = sub.tocoo()
+    if coo.nnz == 0:
+        return out
     pos = np.asarray(P[coo.row, coo.col]).ravel().astype(np.int64) - 1
     assert (pos >= 0).all()
     out[pos] = coo.data
     return out
+
+
+def _synthetic_worker(rank, world, port, q):
+    """Structured synthetic annulus, file-order ('input') partition = z-slabs: SpMV + PEP solve."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helmholtz_x_b200 import eigensolvers, synthetic
+        from helmholtz_x_b200.dist import DistSpace, Partition
+        from helmholtz_x_b200.operators import Mat, OperatorSet
+        from oracle.host_backend import HostBackend
+        from oracle import hx_oracle as ox
+        g = synthetic.annulus_grid(5, 32, 14)
+        m = ox.Mesh(g["x"], g["cells"].astype(np.int64), g["cell_tags"], g["facets"].astype(np.int64), g["facet_tags"])
+        c = synthetic.annulus_sound_speed(g["x"], g["cells"])
+        ops_o = ox.acoustic_matrices(m, {11: {"Robin": -0.875 - 0.2j}}, c, 1, c_is_dg0=True)
+        part = Partition(m.x, m.cells, world, rank, "input", m.facets)
+        assert len(part.neighbours()) == 1
+        be = HostBackend()
+        Vloc = _FakeVloc(be, part, ops_o.A, m.x)
+        space = DistSpace(part, Vloc)
+        vals = {k: torch.from_numpy(_sub_values(part, M, Vloc.pattern())) for k, M in
+                (("A", ops_o.A.real), ("C", ops_o.C.real), ("B", ops_o.B))}
+        ops = OperatorSet(space, space.own_values(vals["A"]), space.own_values(vals["C"]), space.own_values(vals["B"]))
+        A, B, C = Mat(ops, {"A": 1.0}), Mat(ops, {"B": 1.0}), Mat(ops, {"C": 1.0})
+        target = 3225.12 + 481.0j
+        E = eigensolvers.pep_solver(A, B, C, target, nev=2)
+        Eo = ox.pep_solve(ops_o.A, ops_o.B, ops_o.C, target, 2)
+        assert abs(E.getEigenpair(0) - Eo.eigenvalues[0]) / abs(Eo.eigenvalues[0]) < 1e-8
+        q.put((rank, "ok", ops.stats["inner_iterations"]))
+    except Exception:      # noqa: BLE001
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
 
 
 def _worker(rank, world, port, ordering, q):
@@ -151,3 +189,17 @@ def test_two_rank_partitioned_solve_matches_goldens(ordering):
     for rank, status, info in res:
         assert status == "ok", f"rank {rank}: {info}"
     print("inner GMRES iterations per rank:", [info for _, _, info in res])
+
+
+def test_two_rank_slab_partition_of_structured_annulus():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_synthetic_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in res:
+        assert status == "ok", f"rank {rank}: {info}"
