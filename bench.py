@@ -24,9 +24,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if any(a.startswith("--dofs") for a in sys.argv) and any(len(a) >= 7 and a.isdigit() and int(a) >= 5_000_000 for a in sys.argv):
-    # very large runs: the set-up SpGEMM temporaries fragment the caching allocator badly
-    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 
 import numpy as np  # noqa: E402
 

@@ -146,10 +146,8 @@ class CudaBackend:
                   _c2(ca), _c2(cb), _c2(cc), out.data_ptr(), self.stream)
         return out
 
-    def lowrank_dots(self, lr: LowRank, x, t, transpose=False):
-        """t_f = right_f^T x  (transpose=True uses the left vectors: adjoint problem)."""
-        if transpose:
-            raise NotImplementedError
+    def lowrank_dots(self, lr: LowRank, x, t):
+        """t_f = right_f^T x  (the adjoint problem passes a LowRank with the roles swapped)."""
         _lib.call("hx_lowrank_dots", lr.r, lr.rptr.data_ptr(), lr.ridx.data_ptr(), lr.rval.data_ptr(), x.data_ptr(),
                   t.data_ptr(), self.stream)
         return t

@@ -11,7 +11,7 @@ __device__ __forceinline__ int ilu_find(const int* __restrict__ indices, int lo,
         const int mid = (lo + hi) >> 1;
         if (indices[mid] < col) lo = mid + 1; else hi = mid;
     }
-    return (lo < hi || true) ? lo : -1;
+    return lo;
 }
 
 // one warp per row of the level

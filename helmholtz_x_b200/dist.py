@@ -229,7 +229,7 @@ class DistBackend:
             dist.all_reduce(nrm2[:1])
         return w
 
-    def lowrank_dots(self, lr, x, t, transpose=False):
+    def lowrank_dots(self, lr, x, t):
         self.local.lowrank_dots(lr, x, t)
         if self.part.world > 1:
             dist.all_reduce(torch.view_as_real(t[:max(lr.r, 1)]))

@@ -49,6 +49,7 @@ class _Handle:
     def destroy(self):
         self._X = None
         self._Y = None
+        self._Xfull = None
         return self
 
     def _vector(self, X, i, vr):

@@ -51,10 +51,7 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
     V, w = basis.V, basis.w
     z = work if work is not None else be.zeros(n)
     x.zero_()
-    r = V[0]
-    r.copy_(b)
     nb = be.zeros(2)
-    nbr = torch.view_as_real(nb)
     be.multi_dot(b.view(1, -1), 1, b, nb)
     bnorm = float(np.sqrt(nb[:1].cpu().numpy()[0].real))
     if bnorm == 0.0:

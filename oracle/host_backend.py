@@ -58,7 +58,7 @@ class HostBackend:
         out.copy_(r)
         return out
 
-    def lowrank_dots(self, lr, x, t, transpose=False):
+    def lowrank_dots(self, lr, x, t):
         xn = x.numpy()
         for f in range(lr.r):
             s, e = int(lr.rptr[f]), int(lr.rptr[f + 1])
