@@ -72,6 +72,7 @@ SIGNATURES = {
     "hx_flame_right": [i32, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp],
     "hx_locate_points": [i64, vp, vp, i32, vp, f64, vp, vp],
     "hx_point_dphidz": [i32, vp, vp, i32, vp, vp, vp, vp],
+    "hx_shape_derivative": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_threshold": [i64, vp, f64, vp],
 }
 _RESTYPES = {"hx_last_error": C.c_char_p, "hx_launch_count": i64, "hx_reduce_scratch_bytes": i64,

@@ -468,6 +468,113 @@ __global__ void point_dphidz_kernel(const double* __restrict__ x, const int* __r
     }
 }
 
+// ---------------------------------------------------------------------------------
+// (f-1) shape-derivative boundary integral  int (V.n) div(conj(p_adj) c^2 grad p) ds
+// (helmholtz_x/shape_derivatives.py:12-37).  One thread per facet, Dunavant 7-point
+// degree-5 rule (exact for P2 p, P1 c, P1 V), single CTA, fixed-order reduction.
+// ---------------------------------------------------------------------------------
+template <int DEG>
+__global__ void __launch_bounds__(1024)
+shape_derivative_kernel(int n_sel, const int* __restrict__ sel, const double* __restrict__ x,
+                        const int* __restrict__ cells, const int* __restrict__ cell_dofs,
+                        const int* __restrict__ facets, const int* __restrict__ facet_cell,
+                        const double* __restrict__ V, const double2* __restrict__ p, const double2* __restrict__ pa,
+                        const double* __restrict__ cn, double2* __restrict__ out) {
+    constexpr int ND = (DEG == 1) ? 4 : 10;
+    const double qa[7][3] = {{1.0 / 3, 1.0 / 3, 1.0 / 3},
+                             {0.059715871789770, 0.470142064105115, 0.470142064105115},
+                             {0.470142064105115, 0.059715871789770, 0.470142064105115},
+                             {0.470142064105115, 0.470142064105115, 0.059715871789770},
+                             {0.797426985353087, 0.101286507323456, 0.101286507323456},
+                             {0.101286507323456, 0.797426985353087, 0.101286507323456},
+                             {0.101286507323456, 0.101286507323456, 0.797426985353087}};
+    const double qw[7] = {0.225, 0.132394152788506, 0.132394152788506, 0.132394152788506,
+                          0.125939180544827, 0.125939180544827, 0.125939180544827};
+    double2 acc = make_double2(0.0, 0.0);
+    for (int t = threadIdx.x; t < n_sel; t += blockDim.x) {
+        const int f = sel[t];
+        const int* fv = facets + 3LL * f;
+        const int cell = facet_cell[f];
+        const int* cv = cells + 4LL * cell;
+        const TetGeom g = tet_geometry(x, cv);
+        // outward unit normal
+        const double ax = x[3 * fv[0]], ay = x[3 * fv[0] + 1], az = x[3 * fv[0] + 2];
+        const double ux = x[3 * fv[1]] - ax, uy = x[3 * fv[1] + 1] - ay, uz = x[3 * fv[1] + 2] - az;
+        const double vx = x[3 * fv[2]] - ax, vy = x[3 * fv[2] + 1] - ay, vz = x[3 * fv[2] + 2] - az;
+        double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+        const double nn = sqrt(nx * nx + ny * ny + nz * nz);
+        const double area = 0.5 * nn;
+        nx /= nn; ny /= nn; nz /= nn;
+        double cx = 0, cy = 0, cz = 0, fx = 0, fy = 0, fz = 0;
+        for (int k = 0; k < 4; ++k) { cx += 0.25 * x[3 * cv[k]]; cy += 0.25 * x[3 * cv[k] + 1]; cz += 0.25 * x[3 * cv[k] + 2]; }
+        for (int k = 0; k < 3; ++k) { fx += x[3 * fv[k]] / 3; fy += x[3 * fv[k] + 1] / 3; fz += x[3 * fv[k] + 2] / 3; }
+        if (nx * (fx - cx) + ny * (fy - cy) + nz * (fz - cz) < 0) { nx = -nx; ny = -ny; nz = -nz; }
+        int loc[3];
+        for (int k = 0; k < 3; ++k) { loc[k] = 0; for (int a = 0; a < 4; ++a) if (cv[a] == fv[k]) loc[k] = a; }
+        const int* dofs = cell_dofs + (long long)ND * cell;
+        double cc[4];
+        for (int a = 0; a < 4; ++a) cc[a] = cn[cv[a]];
+        double gcx = 0, gcy = 0, gcz = 0;
+        for (int a = 0; a < 4; ++a) { gcx += cc[a] * g.G[a][0]; gcy += cc[a] * g.G[a][1]; gcz += cc[a] * g.G[a][2]; }
+        double2 lap = make_double2(0.0, 0.0);
+        if (DEG == 2) {
+            for (int a = 0; a < ND; ++a) {
+                double l;
+                if (a < 4) l = 4.0 * (g.G[a][0] * g.G[a][0] + g.G[a][1] * g.G[a][1] + g.G[a][2] * g.G[a][2]);
+                else { int pp, qq; tet_edge(a - 4, pp, qq); l = 8.0 * (g.G[pp][0] * g.G[qq][0] + g.G[pp][1] * g.G[qq][1] + g.G[pp][2] * g.G[qq][2]); }
+                const double2 pv = p[dofs[a]];
+                lap.x += l * pv.x; lap.y += l * pv.y;
+            }
+        }
+        for (int q = 0; q < 7; ++q) {
+            double L[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 3; ++k) L[loc[k]] = qa[q][k];
+            double2 pq = make_double2(0, 0), aq = make_double2(0, 0);
+            double2 gp[3] = {make_double2(0, 0), make_double2(0, 0), make_double2(0, 0)};
+            double2 ga[3] = {make_double2(0, 0), make_double2(0, 0), make_double2(0, 0)};
+            for (int a = 0; a < ND; ++a) {
+                double phi, gr[3];
+                if (DEG == 1) { phi = L[a]; gr[0] = g.G[a][0]; gr[1] = g.G[a][1]; gr[2] = g.G[a][2]; }
+                else {
+                    if (a < 4) phi = L[a] * (2.0 * L[a] - 1.0);
+                    else { int pp, qq; tet_edge(a - 4, pp, qq); phi = 4.0 * L[pp] * L[qq]; }
+                    p2_grad(g, L, a, gr);
+                }
+                const double2 pv = p[dofs[a]];
+                const double2 av = make_double2(pa[dofs[a]].x, -pa[dofs[a]].y);      // conj(p_adj)
+                pq.x += phi * pv.x; pq.y += phi * pv.y;
+                aq.x += phi * av.x; aq.y += phi * av.y;
+                for (int k = 0; k < 3; ++k) {
+                    gp[k].x += gr[k] * pv.x; gp[k].y += gr[k] * pv.y;
+                    ga[k].x += gr[k] * av.x; ga[k].y += gr[k] * av.y;
+                }
+            }
+            double cval = 0;
+            for (int a = 0; a < 4; ++a) cval += cc[a] * L[a];
+            double2 gagp = make_double2(0, 0), gcgp = make_double2(0, 0);
+            for (int k = 0; k < 3; ++k) { gagp = cadd(gagp, cmul(ga[k], gp[k])); }
+            gcgp.x = gcx * gp[0].x + gcy * gp[1].x + gcz * gp[2].x;
+            gcgp.y = gcx * gp[0].y + gcy * gp[1].y + gcz * gp[2].y;
+            double2 div = cscale(cval * cval, gagp);
+            div = cadd(div, cscale(2.0 * cval, cmul(aq, gcgp)));
+            div = cadd(div, cscale(cval * cval, cmul(aq, lap)));
+            double vn = 0;
+            for (int a = 0; a < 4; ++a)
+                vn += L[a] * (V[3 * cv[a]] * nx + V[3 * cv[a] + 1] * ny + V[3 * cv[a] + 2] * nz);
+            acc = cadd(acc, cscale(qw[q] * area * vn, div));
+        }
+    }
+    __shared__ double2 sm[32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s = cadd(s, sm[w]);
+        out[0] = s;
+    }
+}
+
 __global__ void threshold_kernel(long long n, double* __restrict__ v, double tol) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && fabs(v[i]) < tol) v[i] = 0.0;
@@ -736,6 +843,21 @@ extern "C" int hx_point_dphidz(int degree, const double* x, const int32_t* cells
     else
         return fail(HX_ERR_ARG, "hx_point_dphidz: degree must be 1 or 2%s%s");
     return check_launch("point_dphidz_kernel");
+}
+
+extern "C" int hx_shape_derivative(int degree, int n_sel, const int32_t* sel, const double* x, const int32_t* cells,
+                                   const int32_t* cell_dofs, const int32_t* facets, const int32_t* facet_cell,
+                                   const double* V, const double* p, const double* p_adj, const double* c_nodal,
+                                   double* out, hx_stream_t stream) {
+    if (degree == 1)
+        shape_derivative_kernel<1><<<1, 1024, 0, (cudaStream_t)stream>>>(n_sel, sel, x, cells, cell_dofs, facets, facet_cell, V,
+                                                                       (const double2*)p, (const double2*)p_adj, c_nodal, (double2*)out);
+    else if (degree == 2)
+        shape_derivative_kernel<2><<<1, 1024, 0, (cudaStream_t)stream>>>(n_sel, sel, x, cells, cell_dofs, facets, facet_cell, V,
+                                                                       (const double2*)p, (const double2*)p_adj, c_nodal, (double2*)out);
+    else
+        return fail(HX_ERR_ARG, "hx_shape_derivative: degree must be 1 or 2%s%s");
+    return check_launch("shape_derivative_kernel");
 }
 
 extern "C" int hx_threshold(int64_t n, double* v, double tol, hx_stream_t stream) {

@@ -216,10 +216,10 @@ def results(E):
         print()
 
 
-def eps_solver(A, C, target, nev, two_sided=False, print_results=False, v0=None):
+def eps_solver(A, C, target, nev, two_sided=False, print_results=False, v0=None, ncv=None):
     """helmholtz_x/eigensolvers.py:41-67: A x = lambda (-C) x nearest target**2.
-    v0 (extension): optional device start vector."""
-    E = EPS(A, -C, target ** 2, nev, two_sided=two_sided, v0=v0)
+    v0, ncv (extensions): optional device start vector / Krylov basis size."""
+    E = EPS(A, -C, target ** 2, nev, two_sided=two_sided, v0=v0, ncv=ncv)
     info("- EPS solver started.")
     E.solve()
     info("- EPS solver converged. Eigenvalue computed.")
@@ -228,16 +228,24 @@ def eps_solver(A, C, target, nev, two_sided=False, print_results=False, v0=None)
     return E
 
 
-def pep_solver(A, B, C, target, nev, print_results=False, v0=None):
+def pep_solver(A, B, C, target, nev, print_results=False, v0=None, ncv=None):
     """helmholtz_x/eigensolvers.py:69-120: (A + w B + w^2 C) p = 0 nearest target.
-    v0 (extension): optional device start vector of length 2n."""
-    Q = PEP(A, B, C, target, nev, v0=v0)
+    v0, ncv (extensions): optional device start vector of length 2n / Krylov basis size."""
+    Q = PEP(A, B, C, target, nev, v0=v0, ncv=ncv)
     info("- PEP solver started.")
     Q.solve()
     info("- PEP solver converged. Eigenvalue computed.")
     if print_results and rank0():
         results(Q)
     return Q
+
+
+def _iteration_nev(nev, i):
+    """Pairs converged inside the nonlinear iterations: only pair i feeds the recurrence
+    (eigensolvers.py:180-182,245-246,321), so the intermediate linear solves converge pairs
+    0..i plus one guard pair; the handle returned to the caller is re-solved (warm-started)
+    for all nev pairs.  The Krylov basis keeps the size SLEPc derives from the caller's nev."""
+    return min(nev, i + 2), max(2 * nev, nev + 15)
 
 
 def _fmt(tol):
@@ -257,7 +265,8 @@ def fixed_point_iteration_eps(operators, D, target, nev=2, i=0, tol=1e-8, maxite
     f = np.zeros(maxiter, dtype=complex)
     alpha = np.zeros(maxiter, dtype=complex)
     info("--> Fixed point iteration started.\n")
-    E = eps_solver(A, C, target, nev, print_results=print_results)
+    nev_it, ncv = _iteration_nev(nev, i)
+    E = eps_solver(A, C, target, nev_it, print_results=print_results, ncv=ncv)
     eig = E.getEigenvalue(i)
     omega[0] = np.sqrt(eig)
     alpha[0] = 0.5
@@ -284,7 +293,8 @@ def fixed_point_iteration_eps(operators, D, target, nev=2, i=0, tol=1e-8, maxite
             D_Mat = A - D_Mat
         else:
             D_Mat = A + (omega[k] * B) - D_Mat
-        E = eps_solver(D_Mat, C, target, nev, two_sided=two_sided, print_results=print_results, v0=v0)
+        E = eps_solver(D_Mat, C, target, nev_it, two_sided=two_sided, print_results=print_results, v0=v0, ncv=ncv)
+        D_last = D_Mat
         del D_Mat
         eig = E.getEigenvalue(i)
         f[k] = np.sqrt(eig)
@@ -295,6 +305,8 @@ def fixed_point_iteration_eps(operators, D, target, nev=2, i=0, tol=1e-8, maxite
         if rank0():
             print('+ omega = {}  {}j,  |domega| = {:.2e}\n'.format(
                 s.format(omega[k + 1].real), s.format(omega[k + 1].imag), abs(domega)))
+    if nev_it < nev:       # the returned handle carries all nev pairs of the LAST linear problem
+        E = eps_solver(D_last, C, target, nev, two_sided=two_sided, print_results=print_results, v0=E.start_vector(), ncv=ncv)
     E.omega_history = omega[:k + 2].copy()
     return E
 
@@ -308,7 +320,8 @@ def fixed_point_iteration_pep(operators, D, target, nev=2, i=0, tol=1e-8, maxite
     omega = np.zeros(maxiter, dtype=complex)
     f = np.zeros(maxiter, dtype=complex)
     alpha = np.zeros(maxiter, dtype=complex)
-    E = pep_solver(A, B, C, target, nev, print_results=print_results)
+    nev_it, ncv = _iteration_nev(nev, i)
+    E = pep_solver(A, B, C, target, nev_it, print_results=print_results, ncv=ncv)
     eig = E.getEigenpair(i)
     omega[0] = eig
     alpha[0] = .5
@@ -330,7 +343,8 @@ def fixed_point_iteration_pep(operators, D, target, nev=2, i=0, tol=1e-8, maxite
         else:
             raise ValueError("The problem type should be specified as 'direct' or 'adjoint'.")
         D_Mat = A - D_Mat
-        E = pep_solver(D_Mat, B, C, target, nev, print_results=print_results, v0=v0)
+        E = pep_solver(D_Mat, B, C, target, nev_it, print_results=print_results, v0=v0, ncv=ncv)
+        D_last = D_Mat
         eig = E.getEigenpair(i)
         f[k] = eig
         if k != 0:
@@ -340,6 +354,8 @@ def fixed_point_iteration_pep(operators, D, target, nev=2, i=0, tol=1e-8, maxite
         if rank0():
             print('+ omega = {}  {}j,  |domega| = {:.2e}\n'.format(
                 s.format(omega[k + 1].real), s.format(omega[k + 1].imag), abs(domega)))
+    if nev_it < nev:
+        E = pep_solver(D_last, B, C, target, nev, print_results=print_results, v0=E.start_vector(), ncv=ncv)
     E.omega_history = omega[:k + 2].copy()
     return E
 
@@ -368,6 +384,8 @@ def newtonSolver(operators, D, init, nev=2, i=0, tol=1e-3, maxiter=100, print_re
     relaxation = 1.0
     info("-> Newton solver started.\n")
     p = None
+    nev_it, ncv = _iteration_nev(nev, i)
+    v0 = None
     while abs(domega) > tol:
         D.assemble_matrix(omega[k])
         if not B:
@@ -376,7 +394,8 @@ def newtonSolver(operators, D, init, nev=2, i=0, tol=1e-3, maxiter=100, print_re
         else:
             L = A + omega[k] * B + omega[k] ** 2 * C - D.matrix
             dL_domega = B + (2 * omega[k] * C) - D.get_derivative(omega[k])
-        E = eps_solver(L, -C, 0, nev, two_sided=True, print_results=print_results)
+        E = eps_solver(L, -C, 0, nev_it, two_sided=True, print_results=print_results, v0=v0, ncv=ncv)
+        v0 = E.start_vector()
         eig = E.getEigenvalue(i)
         omega_dir, p = normalize_eigenvector(operators.mesh, E, i, degree=1, which='right', print_eigs=False,
                                              matrices=operators)

@@ -99,3 +99,24 @@ def xdmf_writer(name, mesh, function):
                  f'<DataItem Dimensions="{nc} 4" NumberType="Int" Format="HDF">{h5}:/Mesh/Grid/topology</DataItem></Topology>'
                  f'<Geometry GeometryType="XYZ"><DataItem Dimensions="{n} 3" Format="HDF">{h5}:/Mesh/Grid/geometry</DataItem>'
                  f'</Geometry>{attr("real")}{attr("imag")}</Grid></Domain></Xdmf>')
+
+
+def write_mesh_xdmf(name, x, cells, cell_tags, facets, facet_tags):
+    """Write the XDMF/HDF5 mesh pair XDMFReader expects (the layout meshio produces in the
+    reference's write_xdmf_mesh, io_utils.py:98-139): name.{xdmf,h5} with points / tetrahedra /
+    cell tags and name_tags.{xdmf,h5} with points / boundary triangles / facet tags."""
+    base = os.path.basename(name)
+    x = np.asarray(x, np.float64)
+    for suffix, conn, tags, ttype, npe in (("", cells, cell_tags, "Tetrahedron", 4), ("_tags", facets, facet_tags, "Triangle", 3)):
+        conn = np.asarray(conn, np.int64)
+        tags = np.asarray(tags, np.int64)
+        h5 = base + suffix + ".h5"
+        write_h5(name + suffix + ".h5", {"/data0": x, "/data1": conn, "/data2": tags})
+        with open(name + suffix + ".xdmf", "w") as fh:
+            fh.write(f'<Xdmf Version="3.0"><Domain><Grid Name="Grid"><Geometry GeometryType="XYZ">'
+                     f'<DataItem DataType="Float" Dimensions="{len(x)} 3" Format="HDF" Precision="8">{h5}:/data0</DataItem>'
+                     f'</Geometry><Topology TopologyType="{ttype}" NumberOfElements="{len(conn)}" NodesPerElement="{npe}">'
+                     f'<DataItem DataType="Int" Dimensions="{len(conn)} {npe}" Format="HDF" Precision="8">{h5}:/data1</DataItem>'
+                     f'</Topology><Attribute Name="name_to_read" AttributeType="Scalar" Center="Cell">'
+                     f'<DataItem DataType="Int" Dimensions="{len(conn)}" Format="HDF" Precision="8">{h5}:/data2</DataItem>'
+                     f'</Attribute></Grid></Domain></Xdmf>')

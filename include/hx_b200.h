@@ -238,6 +238,14 @@ int hx_locate_points(int64_t n_cells, const double* x_f64, const int32_t* cells,
                      const double* points_f64, double tol, int32_t* owner, hx_stream_t stream);
 int hx_point_dphidz(int degree, const double* x_f64, const int32_t* cells, int n_points,
                     const double* points_f64, const int32_t* owner, double* out_np_by_nd, hx_stream_t stream);
+/* adjoint sensitivity tail (helmholtz_x/shape_derivatives.py:12-37):
+ * out[0] = int over the listed boundary facets of (V.n) div(conj(p_adj) c^2 grad p) ds,
+ * V P1 nodal (n_nodes x 3), c P1 nodal, p / p_adj complex128 in the degree-`degree` space,
+ * facet_cell = owning cell of every boundary facet. */
+int hx_shape_derivative(int degree, int n_sel, const int32_t* sel, const double* x_f64, const int32_t* cells,
+                        const int32_t* cell_dofs, const int32_t* facets, const int32_t* facet_cell,
+                        const double* V_f64, const double* p_c128, const double* p_adj_c128,
+                        const double* c_nodal_f64, double* out_c128, hx_stream_t stream);
 /* |v|<tol -> 0 (flame_matrices.py:67-68; values are real) */
 int hx_threshold(int64_t n, double* v_f64, double tol, hx_stream_t stream);
 

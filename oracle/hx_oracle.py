@@ -908,3 +908,64 @@ def fused_apply(ops: Operators, flame, sigma, ftf, x, problem_type="direct"):
         Lf, Rf = flame.factors(problem_type)
         y = y - ftf * (Lf @ (Rf.T @ x))
     return y
+
+
+# ---------------------------------------------------------------------------
+# (f-1) adjoint sensitivity tail: boundary shape-derivative integral
+# ---------------------------------------------------------------------------
+
+
+def facet_normals(mesh: Mesh):
+    """Outward unit normals of the tagged boundary facets (UFL FacetNormal)."""
+    X = mesh.x[mesh.facets]
+    nrm = np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    owner = facet_owner_cells(mesh)
+    centroid = mesh.x[mesh.cells[owner]].mean(axis=1)
+    sign = np.sign(np.einsum("fi,fi->f", nrm, X.mean(axis=1) - centroid))
+    return nrm * sign[:, None]
+
+
+def shape_derivative(space: Space, tag, V_nodal, p_dir, p_adj_normalized, c_nodal):
+    """int_{ds(tag)} (V.n) div( conj(p_adj) c^2 grad p ) ds  for one displacement field V
+    (helmholtz_x/shape_derivatives.py:12-37: G_neu = div(p_adj_conj * c**2 * grad(p_dir)), the
+    form inner(V_ffd, normal) * G_neu * ds(tag)).  V, c are P1 nodal; p, p_adj live in `space`.
+    Evaluated in the owning cell of each facet with a degree-7 triangle rule."""
+    mesh = space.mesh
+    sel = np.flatnonzero(mesh.facet_tags == tag)
+    owner = facet_owner_cells(mesh)[sel]
+    vol, G = geometry(mesh)
+    nrm = facet_normals(mesh)[sel]
+    area = facet_areas(mesh)[sel]
+    Lq, wq = tri_rule(4)
+    fac = mesh.facets[sel]
+    cells = mesh.cells[owner]
+    # barycentric coordinates (in the owner cell) of the facet quadrature points
+    loc = np.array([[int(np.flatnonzero(cells[f] == fac[f, k])[0]) for k in range(3)] for f in range(len(sel))])
+    pa = np.conj(p_adj_normalized)
+    total = 0.0 + 0.0j
+    for q in range(len(wq)):
+        L = np.zeros((len(sel), 4))
+        for k in range(3):
+            L[np.arange(len(sel)), loc[:, k]] = Lq[q, k]
+        val = np.zeros(len(sel), complex)
+        for f in range(len(sel)):
+            Gc = G[owner[f]]                                   # (4,3) grad L_a
+            phi, d = tabulate(space.degree, L[f][None, :])
+            dofs = space.cell_dofs[owner[f]]
+            gphi = d[0] @ Gc                                   # (nd,3) physical gradients
+            p, gp = phi[0] @ p_dir[dofs], gphi.T @ p_dir[dofs]
+            q_, gq = phi[0] @ pa[dofs], gphi.T @ pa[dofs]
+            cc = c_nodal[cells[f]]
+            cval, gc = L[f] @ cc, Gc.T @ cc
+            lap = 0.0
+            if space.degree == 2:
+                # Laplacian of P2 basis: vertex a: 4 |G_a|^2 ; edge (a,b): 8 G_a.G_b
+                GG = Gc @ Gc.T
+                lapphi = np.array([4 * GG[a, a] for a in range(4)] + [8 * GG[a, b] for a, b in TET_EDGES])
+                lap = lapphi @ p_dir[dofs]
+            div = cval ** 2 * (gq @ gp) + q_ * 2 * cval * (gc @ gp) + q_ * cval ** 2 * lap
+            Vq = L[f] @ V_nodal[cells[f]]
+            val[f] = (Vq @ nrm[f]) * div
+        total += wq[q] * (area * val).sum()
+    return total

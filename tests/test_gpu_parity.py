@@ -505,6 +505,58 @@ def test_manufactured_config2_impedance_sweep():
         assert abs(E.getEigenpair(0) - Eo.eigenvalues[0]) / abs(Eo.eigenvalues[0]) < EIG_RTOL
 
 
+@pytest.mark.parametrize("degree", [1, 2])
+def test_shape_derivative_boundary_integral_matches_oracle(degree):
+    """(f-1) helmholtz_x/shape_derivatives.py:12-37: int (V.n) div(conj(p_adj) c^2 grad p) ds on the
+    lateral wall of the RijkeFFD tube for a radial and an axial-bump displacement field."""
+    from helmholtz_x_b200.shape_derivatives import boundary_shape_integral
+    case = degree_case("rijkeffd", degree)
+    m = case.mesh
+    mesh = gpu_mesh(case)
+    sp_ = ox.function_space(m, degree)
+    rng = np.random.default_rng(12)
+    p = rng.standard_normal(sp_.n) + 1j * rng.standard_normal(sp_.n)
+    pa = rng.standard_normal(sp_.n) + 1j * rng.standard_normal(sp_.n)
+    c = ox.sound_speed_variable_gamma(case.T)
+    for V in (np.stack([m.x[:, 0], m.x[:, 1], 0 * m.x[:, 2]], 1),
+              np.stack([m.x[:, 0], m.x[:, 1], 0 * m.x[:, 2]], 1) * np.exp(-((m.x[:, 2] - 0.5) / 0.1) ** 2)[:, None]):
+        got = boundary_shape_integral(mesh, degree, 1, V, p, pa, c)
+        ref = ox.shape_derivative(sp_, 1, V, p, pa, c)
+        assert abs(got - ref) < 1e-11 * abs(ref), (got, ref)
+
+
+def test_xdmf_reader_writer_round_trip_drives_a_solve(tmp_path):
+    """(f-2) io_utils: XDMFReader on a meshio-layout XDMF/HDF5 pair, the reference's driver flow
+    (XDMFReader -> c_step -> AcousticMatrices -> eps_solver -> normalize_eigenvector -> xdmf_writer),
+    and the DOLFINx-layout result file read back."""
+    from helmholtz_x_b200.acoustic_matrices import AcousticMatrices
+    from helmholtz_x_b200.eigensolvers import eps_solver
+    from helmholtz_x_b200.eigenvectors import normalize_eigenvector
+    from helmholtz_x_b200.h5lite import H5File
+    from helmholtz_x_b200.io_utils import XDMFReader, write_mesh_xdmf, xdmf_writer
+    from helmholtz_x_b200.parameters_utils import c_step
+    m = cases.mesh("rijke3d")
+    stem = str(tmp_path / "mesh")
+    write_mesh_xdmf(stem, m.x, m.cells, m.cell_tags, m.facets, m.facet_tags)
+    geo = XDMFReader(stem)
+    mesh, subdomains, facet_tags = geo.getAll()
+    assert geo.getInfo() == 8530 and mesh.n_nodes == 2426
+    assert np.array_equal(mesh.cells, m.cells) and np.array_equal(mesh.facet_tags, m.facet_tags)
+    c_u = np.sqrt(1.4 * 1e5 / 1.22)
+    c = c_step(mesh, np.array([[0.0, 0.0, 0.25]]), c_u, c_u)
+    matrices = AcousticMatrices(mesh, facet_tags, {1: {'Neumann'}, 2: {'Neumann'}, 3: {'Neumann'}}, c, degree=1)
+    E = eps_solver(matrices.A, matrices.C, 200 * 2 * np.pi, nev=2)
+    omega, p = normalize_eigenvector(mesh, E, 0, degree=1, which='right')
+    gold = np.sqrt(G["rijke3d_passive_eps"]["lambdas"][0])
+    lam = [abs(np.sqrt(E.getEigenvalue(i)) - gold) / gold for i in range(2)]
+    assert min(lam) < EIG_RTOL
+    xdmf_writer(str(tmp_path / "p"), mesh, p)
+    f = H5File(str(tmp_path / "p.h5"))
+    assert np.array_equal(f["/Mesh/Grid/topology"], m.cells)
+    back = f["/Function/real_f/0"][:, 0] + 1j * f["/Function/imag_f/0"][:, 0]
+    assert np.array_equal(back, p.x.array)
+
+
 def test_fpi_annulus_config3_matches_golden():
     """.../fullAnnulus/Results/Active/FPI/active.log:43-92 and eigenvalues_dir.txt"""
     case = cases.annulus()
