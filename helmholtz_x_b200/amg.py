@@ -116,6 +116,10 @@ def _values_on(pattern_keys, T, n_cols):
     return out
 
 
+def _real(v):
+    return v.real.contiguous() if v.is_complex() else v
+
+
 class Level:
     pass
 
@@ -176,7 +180,7 @@ class AMG:
                 except Overflow:
                     pass          # a product row exceeds the kernel's shared-memory budget: library path below
             T = torch.sparse_coo_tensor(torch.stack([torch.arange(n, device=dev), agg]), tval, size=(n, nc)).coalesce()
-            kval = -a_re + tau * c_re
+            kval = -_real(a_re) + tau * _real(c_re)
             K = _to_coo(pat, kval)
             d = _diag(pat.with_values(kval))
             rows = K.indices()[0]
@@ -218,9 +222,12 @@ class AMG:
                 if vals.is_cuda and n > 3_000_000:
                     torch.cuda.empty_cache()      # the SpGEMM temporaries are GBs at 10 M DoF
                 return Z
-            Ac = galerkin(a_re)
-            Cc = galerkin(c_re)
+            Ac = galerkin(_real(a_re))
+            Cc = galerkin(_real(c_re))
             mats = [Ac, Cc]
+            Ai = galerkin(a_re.imag.contiguous()) if a_re.is_complex() else None
+            Ci = galerkin(c_re.imag.contiguous()) if c_re.is_complex() else None
+            mats += [m_ for m_ in (Ai, Ci) if m_ is not None]
             if b_cx is not None:
                 Br = galerkin(b_cx.real.contiguous())
                 Bi = galerkin(b_cx.imag.contiguous())
@@ -236,6 +243,10 @@ class AMG:
                             torch.zeros(keys.numel(), dtype=f64, device=dev))
             a_re = _values_on(keys, Ac, nc)
             c_re = _values_on(keys, Cc, nc)
+            if Ai is not None:
+                a_re = torch.complex(a_re, _values_on(keys, Ai, nc))
+            if Ci is not None:
+                c_re = torch.complex(c_re, _values_on(keys, Ci, nc))
             if b_cx is not None:
                 b_cx = torch.complex(_values_on(keys, Br, nc), _values_on(keys, Bi, nc))
             csum = torch.zeros(nc, 3, dtype=f64, device=dev)
@@ -265,7 +276,7 @@ class AMG:
         from . import spgemm
         n, dev = pat.n_rows, a_re.device
         self.native_levels = getattr(self, "native_levels", 0) + 1
-        kval = -a_re + tau * c_re
+        kval = -_real(a_re) + tau * _real(c_re)
         rows = _rows_of(pat.indptr, pat.nnz)
         d = _diag(pat.with_values(kval))
         S = pat.with_values((kval / d[rows]).contiguous())
@@ -294,8 +305,10 @@ class AMG:
         def galerkin(vals):
             yv = spgemm.numeric(be, pat.with_values(vals.contiguous()), P, yp[0], yp[1], out=ybuf)
             return spgemm.numeric(be, R, CsrMatrix(n, nc, yp[0], yp[1], yv), zp[0], zp[1]).clone()
-        a_c = galerkin(a_re)
-        c_c = galerkin(c_re)
+        def galerkin_any(vals):
+            return torch.complex(galerkin(vals.real), galerkin(vals.imag)) if vals.is_complex() else galerkin(vals)
+        a_c = galerkin_any(a_re)
+        c_c = galerkin_any(c_re)
         b_c = None
         if b_cx is not None:
             b_c = torch.complex(galerkin(b_cx.real), galerkin(b_cx.imag))

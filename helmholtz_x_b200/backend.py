@@ -140,10 +140,19 @@ class CudaBackend:
         return y
 
     def combine_abc(self, a, b, c, ca, cb, cc, out):
+        """out = ca*a + cb*b + cc*c on one pattern.  a, c are real (the assembled A, C) and go
+        through one fused kernel with the complex b; complex a / c (Bloch-reduced operators)
+        are added with the axpby kernel."""
         nnz = out.numel()
-        _lib.call("hx_combine_abc", nnz, a.data_ptr() if a is not None else None,
-                  b.data_ptr() if b is not None else None, c.data_ptr() if c is not None else None,
+        ar = a if (a is not None and a.dtype == f64) else None
+        cr = c if (c is not None and c.dtype == f64) else None
+        _lib.call("hx_combine_abc", nnz, ar.data_ptr() if ar is not None else None,
+                  b.data_ptr() if b is not None else None, cr.data_ptr() if cr is not None else None,
                   _c2(ca), _c2(cb), _c2(cc), out.data_ptr(), self.stream)
+        if a is not None and ar is None:
+            self.axpby(ca, a, 1.0, out)
+        if c is not None and cr is None:
+            self.axpby(cc, c, 1.0, out)
         return out
 
     def lowrank_dots(self, lr: LowRank, x, t):

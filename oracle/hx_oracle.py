@@ -969,3 +969,57 @@ def shape_derivative(space: Space, tag, V_nodal, p_dir, p_adj_normalized, c_noda
             val[f] = (Vq @ nrm[f]) * div
         total += wq[q] * (area * val).sum()
     return total
+
+
+# ---------------------------------------------------------------------------
+# (f-3) Bloch-periodic reduction   (helmholtz_x/bloch_operator.py)
+# ---------------------------------------------------------------------------
+
+
+def bloch_pairs(space: Space, master_tag, slave_tag, N, pairing="geometric", numbering=None, tol=1e-8):
+    """(master dofs, slave dofs) paired.  pairing="geometric": a master dof is the image of its
+    slave under the rotation by -2 pi / N about z.  pairing="sorted" restates the reference:
+    k-th master with k-th slave in ascending dof index (bloch_operator.py:33-40); `numbering`
+    (reference dof index of every dof here) makes that order the reference's DOLFINx order
+    (only 49 % of those pairs are geometric images)."""
+    mesh = space.mesh
+    md = np.unique(space.facet_dofs[mesh.facet_tags == master_tag])
+    sd = np.unique(space.facet_dofs[mesh.facet_tags == slave_tag])
+    assert len(md) == len(sd)
+    if pairing == "sorted":
+        if numbering is not None:
+            md = md[np.argsort(numbering[md])]
+            sd = sd[np.argsort(numbering[sd])]
+        return md, sd
+    from scipy.spatial import cKDTree
+    X = space.dof_x
+    best = None
+    for sgn in (1.0, -1.0):
+        a = sgn * 2 * np.pi / N
+        Rm = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        d, j = cKDTree(X[sd]).query(X[md] @ Rm.T)
+        if best is None or d.max() < best[0]:
+            best = (d.max(), j)
+    assert best[0] < tol * max(np.abs(X).max(), 1.0) * 1e3, f"master/slave faces are not rotation images (max dist {best[0]})"
+    return md, sd[best[1]]
+
+
+def bloch_maps(n, masters, slaves, N, b=1.0):
+    """BN (n x n_red) and NB = BN^H (bloch_operator.py:42-68): reduced dofs = all but the
+    masters; full[master_k] = f_b * reduced[slave_k], f_b = exp(2 pi i b / N)."""
+    f_b = np.exp(b * 1j * 2 * np.pi / N)
+    keep = np.ones(n, bool)
+    keep[masters] = False
+    red = -np.ones(n, np.int64)
+    red[keep] = np.arange(keep.sum())
+    rows = np.concatenate([np.flatnonzero(keep), masters])
+    cols = np.concatenate([red[keep], red[slaves]])
+    vals = np.concatenate([np.ones(keep.sum(), complex), np.full(len(masters), f_b)])
+    BN = sp.csr_matrix((vals, (rows, cols)), shape=(n, int(keep.sum())))
+    return BN, BN.conj().T.tocsr()
+
+
+def blochify(Mx, BN, NB):
+    out = (NB @ Mx @ BN).tocsr()
+    out.sort_indices()
+    return out

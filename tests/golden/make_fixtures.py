@@ -106,6 +106,9 @@ def main():
     g["flamedduct_active_fpi"] = dict(source=D + ":28-56", omegas=omegas_from_log(D, 21, 56))
     B = "AnnularCombustor/Micca/bloch/Results/Passive/passive.log"
     g["bloch_passive"] = dict(source=B + ":27-31", omegas=[2931.177998, 4633.352640, 11107.674019])
+    BA = "AnnularCombustor/Micca/bloch/Results/Active/active.log"
+    g["bloch_active_fpi"] = dict(source=BA + ":38-75", omegas=omegas_from_log(BA, 38, 75),
+                                 final=[3235.145363, 436.054594])
     # config 2: manufactured 2-D duct, analytic dispersion roots written by the reference's MATLAB script
     rows = [ln.split() for ln in open(REF + "manufacturedSolution/matlab_data/analytical.txt").read().splitlines() if ln.strip()]
     sel = [0, 60, 140, 260, 340, 399]
@@ -120,7 +123,8 @@ def main():
 
     # golden eigenvectors (DOLFINx node order + geometry)
     for name, path in {"rijke3d_active": L + "Active/p.h5", "rijke3d_passive": L + "Passive/p.h5",
-                       "rijkeffd_dir": F + "p_dir.h5", "rijkeffd_adj": F + "p_adj.h5"}.items():
+                       "rijkeffd_dir": F + "p_dir.h5", "rijkeffd_adj": F + "p_adj.h5",
+                       "bloch_passive1": "AnnularCombustor/Micca/bloch/Results/Passive/p_1.h5"}.items():
         f = H5File(REF + path)
         re_k = [k for k in f.keys() if "/real_" in k][0]
         im_k = [k for k in f.keys() if "/imag_" in k][0]
