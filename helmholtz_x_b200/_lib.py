@@ -42,6 +42,7 @@ SIGNATURES = {
     "hx_jacobi_sweep_c": [i32, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp],
     "hx_sell_gather_c": [i64, vp, vp, vp, vp],
     "hx_combine_abc": [i64, vp, vp, vp, vp, vp, vp, vp, vp],
+    "hx_combine_zzz": [i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_lowrank_dots": [i32, vp, vp, vp, vp, vp, vp],
     "hx_lowrank_update": [i32, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_reduce_scratch_bytes": [i32],

@@ -140,19 +140,17 @@ class CudaBackend:
         return y
 
     def combine_abc(self, a, b, c, ca, cb, cc, out):
-        """out = ca*a + cb*b + cc*c on one pattern.  a, c are real (the assembled A, C) and go
-        through one fused kernel with the complex b; complex a / c (Bloch-reduced operators)
-        are added with the axpby kernel."""
+        """out = ca*a + cb*b + cc*c on one pattern.  a, c real (the assembled A, C) with complex b,
+        or all complex (Bloch-reduced operators); one fused kernel either way."""
         nnz = out.numel()
-        ar = a if (a is not None and a.dtype == f64) else None
-        cr = c if (c is not None and c.dtype == f64) else None
-        _lib.call("hx_combine_abc", nnz, ar.data_ptr() if ar is not None else None,
-                  b.data_ptr() if b is not None else None, cr.data_ptr() if cr is not None else None,
-                  _c2(ca), _c2(cb), _c2(cc), out.data_ptr(), self.stream)
-        if a is not None and ar is None:
-            self.axpby(ca, a, 1.0, out)
-        if c is not None and cr is None:
-            self.axpby(cc, c, 1.0, out)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        cplx = [t.dtype == c128 for t in (a, c) if t is not None]
+        if cplx and all(cplx):
+            _lib.call("hx_combine_zzz", nnz, ptr(a), ptr(b), ptr(c), _c2(ca), _c2(cb), _c2(cc), out.data_ptr(), self.stream)
+        elif not any(cplx):
+            _lib.call("hx_combine_abc", nnz, ptr(a), ptr(b), ptr(c), _c2(ca), _c2(cb), _c2(cc), out.data_ptr(), self.stream)
+        else:
+            raise TypeError("combine_abc: A and C must both be real or both complex")
         return out
 
     def lowrank_dots(self, lr: LowRank, x, t):

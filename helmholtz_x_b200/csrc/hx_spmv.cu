@@ -214,6 +214,21 @@ __global__ void combine_abc_kernel(long long nnz, const double* __restrict__ a, 
     }
 }
 
+// all three operands complex (Bloch-reduced A and C are Hermitian, not real)
+__global__ void combine_zzz_kernel(long long nnz, const double2* __restrict__ a, const double2* __restrict__ b,
+                                   const double2* __restrict__ c, double2 ca, double2 cb, double2 cc,
+                                   double2* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) {
+        double2 r = make_double2(0.0, 0.0);
+        if (a) r = cmul(ca, ld_stream(a + i));
+        if (c) r = cadd(r, cmul(cc, ld_stream(c + i)));
+        if (b) r = cadd(r, cmul(cb, ld_stream(b + i)));
+        out[i] = r;
+    }
+}
+
 // ---- matrix-free rank-r flame term ------------------------------------------------
 // one warp per flame f: t_f = r_f^T x   (sparse r_f, fixed reduction order)
 __global__ void lowrank_dots_kernel(int r, const int* __restrict__ rptr, const int* __restrict__ ridx,
@@ -457,6 +472,18 @@ extern "C" int hx_combine_abc(int64_t nnz, const double* a, const double* b, con
     combine_abc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         nnz, a, (const double2*)b, c, ca_h ? h2c(ca_h) : z, cb_h ? h2c(cb_h) : z, cc_h ? h2c(cc_h) : z, (double2*)out);
     return check_launch("combine_abc_kernel");
+}
+
+extern "C" int hx_combine_zzz(int64_t nnz, const double* a, const double* b, const double* c, const double* ca_h,
+                              const double* cb_h, const double* cc_h, double* out, hx_stream_t stream) {
+    if (nnz <= 0) return HX_OK;
+    const double2 z = make_double2(0.0, 0.0);
+    long long blocks = ceil_div<long long>(nnz, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    combine_zzz_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        nnz, (const double2*)a, (const double2*)b, (const double2*)c, ca_h ? h2c(ca_h) : z, cb_h ? h2c(cb_h) : z,
+        cc_h ? h2c(cc_h) : z, (double2*)out);
+    return check_launch("combine_zzz_kernel");
 }
 
 extern "C" int hx_lowrank_dots(int r, const int32_t* rptr, const int32_t* ridx, const double* rval, const double* x,

@@ -89,6 +89,15 @@ class FlameMatrix:
             ValueError("The problem type should be specified as 'direct' or 'adjoint'.")
         info("- Matrix D is assembled.")
 
+    def blochify(self, problem_type='direct'):
+        """Reduce the vector pairs with the Blochifier handed to the constructor (flame_matrices.py:117-127)."""
+        if problem_type == 'direct':
+            self._D_ij = self.bloch_object.blochify(self.submatrices)
+        elif problem_type == 'adjoint':
+            self._D_ij_adj = self.bloch_object.blochify(self.adjoint_submatrices)
+        else:
+            ValueError("The problem type should be specified as 'direct' or 'adjoint'.")
+
     def get_derivative(self, omega):
         dD_domega = self.FTF.derivative(omega) * self._D_ij
         info("- Derivative of matrix D is assembled.")

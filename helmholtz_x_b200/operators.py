@@ -302,6 +302,9 @@ class ShiftedSolver:
         self.P_values, self.P, self.Pop = st["P_values"], st["P"], st["Pop"]
         self.basis, self.work = st["basis"], st["work"]
         self.lowrank = [m for m in lowrank if m.coef != 0 and m.lr.r > 0]
+        if transposed and not getattr(ops, "symmetric", True):
+            raise NotImplementedError("left eigenvectors need the transposed operator; the Bloch-reduced operators are "
+                                      "Hermitian, not symmetric (the reference leaves Blochifier.B_adj unset as well)")
         if transposed:
             self.lowrank = [m.transpose() for m in self.lowrank]
         if self.lowrank:

@@ -108,6 +108,11 @@ int hx_sell_gather_c(int64_t total, const int32_t* src, const double* csr_vals_c
 int hx_combine_abc(int64_t nnz, const double* a_f64, const double* b_c128, const double* c_f64,
                    const double* ca_h, const double* cb_h, const double* cc_h, double* out_c128,
                    hx_stream_t stream);
+/* Same with A, B, C all complex on one pattern (any may be NULL): the Bloch-reduced operators
+ * NB*A*BN, NB*C*BN of helmholtz_x/bloch_operator.py:70-78 are Hermitian, not real. */
+int hx_combine_zzz(int64_t nnz, const double* a_c128, const double* b_c128, const double* c_c128,
+                   const double* ca_h, const double* cb_h, const double* cc_h, double* out_c128,
+                   hx_stream_t stream);
 /* matrix-free flame term (flame_matrices.py:75-108 without the outer product):
  * t_f = sum_k rval[k] x[ridx[k]] over k in [rptr[f], rptr[f+1]);
  * y[lrow[i]] += coef * sum_{k in [lptr[i],lptr[i+1])} lval[k] * t[lcol[k]]  */

@@ -1023,3 +1023,14 @@ def blochify(Mx, BN, NB):
     out = (NB @ Mx @ BN).tocsr()
     out.sort_indices()
     return out
+
+
+def bloch_operators(ops: Operators, BN, NB) -> Operators:
+    """Blochifier.A/.B/.C (bloch_operator.py:70-78); B_adj stays unset as in the reference (:25,:89-90)."""
+    return Operators(ops.space, blochify(ops.A, BN, NB), blochify(ops.B, BN, NB) if ops.B is not None else None, None,
+                     blochify(ops.C, BN, NB), ops.C_nobc, ops.c, ops.gamma)
+
+
+def bloch_flame(flame: Flame, BN, NB) -> Flame:
+    """FlameMatrix.blochify (flame_matrices.py:117-127): NB (l r^T) BN = (NB l)(BN^T r)^T."""
+    return Flame(np.asarray(NB @ flame.left), np.asarray(BN.T @ flame.right), flame.FTF)

@@ -124,7 +124,8 @@ def main():
     # golden eigenvectors (DOLFINx node order + geometry)
     for name, path in {"rijke3d_active": L + "Active/p.h5", "rijke3d_passive": L + "Passive/p.h5",
                        "rijkeffd_dir": F + "p_dir.h5", "rijkeffd_adj": F + "p_adj.h5",
-                       "bloch_passive1": "AnnularCombustor/Micca/bloch/Results/Passive/p_1.h5"}.items():
+                       "bloch_passive1": "AnnularCombustor/Micca/bloch/Results/Passive/p_1.h5",
+                       "bloch_active1": "AnnularCombustor/Micca/bloch/Results/Active/p_1_dir.h5"}.items():
         f = H5File(REF + path)
         re_k = [k for k in f.keys() if "/real_" in k][0]
         im_k = [k for k in f.keys() if "/imag_" in k][0]

@@ -34,7 +34,7 @@ def gpu_ftf(case):
     return nTau(spec[1], spec[2]) if spec[0] == "ntau" else stateSpace(*spec[1:])
 
 
-def gpu_flame(case, mesh=None):
+def gpu_flame(case, mesh=None, bloch_object=None):
     from helmholtz_x_b200.flame_matrices import DistributedFlameMatrix, PointwiseFlameMatrix
     from helmholtz_x_b200.fem import MeshTags
     mesh = mesh or gpu_mesh(case)
@@ -44,4 +44,4 @@ def gpu_flame(case, mesh=None):
         return DistributedFlameMatrix(mesh, w, h, rho, T, case.q_0, case.u_b, ftf, degree=case.degree, gamma=case.gamma)
     h = gpu_field(mesh, case.h, dg0=True)
     return PointwiseFlameMatrix(mesh, MeshTags(mesh.cell_tags), case.x_r, h, case.rho_u, case.q_0, case.u_b, ftf,
-                                degree=case.degree, gamma=case.gamma)
+                                degree=case.degree, bloch_object=bloch_object, gamma=case.gamma)

@@ -19,6 +19,8 @@ class HostSpace:
         self._pattern = (torch.from_numpy(ip.copy()), torch.from_numpy(ix.copy()))
         self.dof_coords = torch.from_numpy(np.ascontiguousarray(space.dof_x))
         self.oracle_space = space
+        self.mesh = space.mesh
+        self.facet_dofs = torch.from_numpy(np.ascontiguousarray(space.facet_dofs))
 
     def pattern(self):
         return self._pattern
@@ -62,6 +64,9 @@ class HostFlame:
         self._D_ij = LowRankMat(n, lr, lrT, 1.0, (L, R))
         self._D_ij_adj = LowRankMat(n, lrT, lr, 1.0, (R, L))
         self.matrix = self.adjoint_matrix = None
+
+    def blochify(self, bloch_object):
+        self._D_ij = bloch_object.blochify(self._D_ij)
 
     def assemble_matrix(self, omega, problem_type='direct'):
         if problem_type == 'direct':

@@ -557,6 +557,76 @@ def test_xdmf_reader_writer_round_trip_drives_a_solve(tmp_path):
     assert np.array_equal(back, p.x.array)
 
 
+def _bloch_setup(pairing):
+    from helmholtz_x_b200.bloch_operator import Blochifier
+    case = cases.bloch()
+    mats = gpu_operators(case)
+    space = ox.function_space(case.mesh, 1)
+    numb = cases.bloch_numbering(space)
+    bl = Blochifier(geometry=gpu_mesh(case), boundary_conditions=case.bcs, N=case.N, passive_matrices=mats,
+                    pairing=pairing, numbering=numb)
+    md, sd = ox.bloch_pairs(space, case.master, case.slave, case.N, pairing=pairing, numbering=numb)
+    BN, NB = ox.bloch_maps(space.n, md, sd, case.N)
+    return case, mats, bl, (md, sd, BN, NB)
+
+
+@pytest.mark.parametrize("pairing", ["sorted", "geometric"])
+def test_bloch_config4_reduced_operators_match_oracle(pairing):
+    """bloch_operator.py:42-78,104-111: NB*M*BN for A, B, C; the pairing itself is index work (bit-exact)."""
+    case, mats, bl, (md, sd, BN, NB) = _bloch_setup(pairing)
+    assert np.array_equal(bl.dofs_master, md) and np.array_equal(bl.dofs_slave, sd)
+    oo = cases.oracle_operators(case)
+    for name, M in (("A", oo.A), ("B", oo.B), ("C", oo.C)):
+        want = ox.blochify(M, BN, NB)
+        got = getattr(bl, name).to_scipy()
+        got.sort_indices()
+        assert got.shape == want.shape
+        assert abs(got - want).max() <= VAL_RTOL * abs(want).max(), name
+    x = np.random.default_rng(1).standard_normal(bl.n_red) + 1j * np.random.default_rng(2).standard_normal(bl.n_red)
+    xin, y = bl.remapper.createVecs()
+    xin.setArray(x)
+    bl.remapper.mult(xin, y)
+    assert np.array_equal(y.array, BN @ x) or relmax(y.array, BN @ x) < 1e-15
+
+
+def test_bloch_config4_passive_and_active_match_golden():
+    """config 4, the reference's drivers bloch/passive.py and bloch/active.py through the product API:
+    Results/Passive/passive.log:27-31 + p_1.h5, Results/Active/active.log:38-75 + p_1_dir.h5."""
+    from helmholtz_x_b200.eigensolvers import eps_solver, fixed_point_iteration
+    from helmholtz_x_b200.eigenvectors import normalize_eigenvector
+    from scipy.spatial import cKDTree
+    case, mats, bl, _ = _bloch_setup("sorted")
+
+    def vs_golden(p, name):
+        gp = np.load(cases.GOLDEN_DIR + "/" + name)
+        d, idx = cKDTree(case.mesh.x).query(gp["geometry"])
+        assert d.max() < 1e-9
+        pm, pg = p.x.array[idx], gp["p"]
+        sgn = 1 if abs(pm[0] - pg[0]) < abs(pm[0] + pg[0]) else -1
+        return np.abs(sgn * pm - pg).max() / np.abs(pg).max()
+
+    E = eps_solver(bl.A, bl.C, case.passive_target, nev=case.passive_nev, print_results=False)
+    for k, g in enumerate(G["bloch_passive"]["omegas"]):
+        omega, p = normalize_eigenvector(mats.mesh, E, k, BlochRemapper=bl.remapper)
+        assert abs(omega - g) <= EIG_RTOL * g + 6e-7, (k, omega, g)          # log prints 6 decimals
+        if k == 0:
+            assert p.x.array.shape == (case.mesh.n_nodes,)
+            assert vs_golden(p, "bloch_passive1_p.npz") < 1e-6
+
+    D = gpu_flame(case, bloch_object=bl)
+    D.assemble_submatrices('direct')
+    D.blochify()
+    assert D.submatrices.n == bl.n_red
+    E = fixed_point_iteration(bl, D, case.target, nev=case.nev, i=0, tol=case.tol)
+    gold = [cases.cplx(p) for p in G["bloch_active_fpi"]["omegas"]]
+    assert len(E.omega_history) == len(gold) + 1
+    _check_history(E.omega_history, gold, rtol=0, atol=6e-4)                 # log prints 3 decimals
+    omega, p = normalize_eigenvector(mats.mesh, E, 0, degree=1, BlochRemapper=bl.remapper)
+    gf = cases.cplx(G["bloch_active_fpi"]["final"])
+    assert abs(omega - gf) <= EIG_RTOL * abs(gf) + 1e-6                      # printed with 6 decimals
+    assert vs_golden(p, "bloch_active1_p.npz") < 1e-6
+
+
 def test_fpi_annulus_config3_matches_golden():
     """.../fullAnnulus/Results/Active/FPI/active.log:43-92 and eigenvalues_dir.txt"""
     case = cases.annulus()

@@ -193,3 +193,51 @@ def test_native_spgemm_coarsening_path_matches_library_path(rijke, monkeypatch):
     c1n = to_sp(nat.levels[1].pattern, nat.levels[1].c)
     c1r = to_sp(ref.levels[1].pattern, ref.levels[1].c)
     assert abs(c1n - c1r).max() < 1e-9 * abs(c1r).max()
+
+
+def test_bloch_reduction_host_logic():
+    """config 4 (Micca sector, N = 16): the product's Blochifier (relabelled CSR entries, no BN/NB
+    products) against the oracle's NB*M*BN, then the reference's passive and active drivers
+    (bloch/passive.py, bloch/active.py) through eps_solver / fixed_point_iteration on the CPU double."""
+    from helmholtz_x_b200.bloch_operator import Blochifier
+    from helmholtz_x_b200.fem import _Vec
+    case = cases.bloch()
+    hops = HostOperators(case)
+    sp_ = hops.oracle.space
+    numb = cases.bloch_numbering(sp_)
+    for pairing in ("sorted", "geometric"):
+        bl = Blochifier(case.mesh, case.bcs, case.N, hops, pairing=pairing, numbering=numb)
+        md, sd = ox.bloch_pairs(sp_, case.master, case.slave, case.N, pairing=pairing, numbering=numb)
+        assert np.array_equal(bl.dofs_master, md) and np.array_equal(bl.dofs_slave, sd)
+        BN, NB = ox.bloch_maps(sp_.n, md, sd, case.N)
+        for name, M in (("A", hops.oracle.A), ("B", hops.oracle.B), ("C", hops.oracle.C)):
+            want = ox.blochify(M, BN, NB)
+            got = getattr(bl, name).to_scipy()
+            assert abs(got - want).max() <= 1e-13 * abs(want).max(), (pairing, name)
+        assert bl.B_adj is None
+        # remapper = BN
+        x = np.random.default_rng(0).standard_normal(bl.n_red) + 0j
+        xin, y = bl.remapper.createVecs()
+        xin.setArray(x)
+        bl.remapper.mult(xin, y)
+        assert np.allclose(y.array, BN @ x, rtol=0, atol=1e-14)
+    # passive: bloch/Results/Passive/passive.log:27-31 (sorted pairing = the reference's)
+    bl = Blochifier(case.mesh, case.bcs, case.N, hops, pairing="sorted", numbering=numb)
+    E = eigensolvers.eps_solver(bl.A, bl.C, case.passive_target, nev=case.passive_nev, print_results=False)
+    for k, g in enumerate(G["bloch_passive"]["omegas"]):
+        assert abs(np.sqrt(E.getEigenvalue(k)) - g) < 1e-6 + 1e-9 * g
+    # active: bloch/Results/Active/active.log:38-75
+    D = HostFlame(case, hops)
+    D.blochify(bl)
+    assert D._D_ij.n == bl.n_red
+    E = eigensolvers.fixed_point_iteration(bl, D, case.target, nev=case.nev, i=0, tol=case.tol)
+    gold = [cases.cplx(p) for p in G["bloch_active_fpi"]["omegas"]]
+    hist = E.omega_history
+    assert len(hist) == len(gold) + 1
+    for a, b in zip(hist[1:], gold):
+        assert abs(a - b) < 6e-4
+    vr, vi = bl.A.createVecs()
+    omega = E.getEigenpair(0, vr, vi)
+    assert abs(omega - cases.cplx(G["bloch_active_fpi"]["final"])) < 2e-6
+    with pytest.raises(NotImplementedError):
+        eigensolvers.eps_solver(bl.A, bl.C, case.passive_target, nev=2, two_sided=True)
