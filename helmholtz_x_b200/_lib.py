@@ -28,6 +28,7 @@ SIGNATURES = {
     "hx_version": [],
     "hx_launch_count": [],
     "hx_launch_count_reset": [],
+    "hx_launch_count_add": [i64],
     "hx_spmv_zz": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "hx_spmv_dz": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "hx_spmv_sell_zz": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
@@ -77,8 +78,8 @@ SIGNATURES = {
     "hx_threshold": [i64, vp, f64, vp],
 }
 _RESTYPES = {"hx_last_error": C.c_char_p, "hx_launch_count": i64, "hx_reduce_scratch_bytes": i64,
-             "hx_launch_count_reset": None}
-_NO_CHECK = {"hx_last_error", "hx_version", "hx_launch_count", "hx_launch_count_reset",
+             "hx_launch_count_reset": None, "hx_launch_count_add": None}
+_NO_CHECK = {"hx_last_error", "hx_version", "hx_launch_count", "hx_launch_count_reset", "hx_launch_count_add",
              "hx_reduce_scratch_bytes", "hx_color_cells_h"}
 
 _lib = None

@@ -19,6 +19,8 @@ prolongation and a dense GEMV on the coarsest level -- all libhx_b200 kernels.
 from __future__ import annotations
 
 import numpy as np
+import os
+
 import torch
 
 from .backend import CsrMatrix
@@ -139,6 +141,10 @@ class AMG:
         it is only a preconditioner; GMRES and everything outside stay complex128."""
         self.be, self.nu, self.omega = be, nu, omega
         self.native_min_rows = 20000
+        # the V-cycle is a fixed sequence of ~25 small launches on fixed buffers: captured once per
+        # shift in a CUDA graph and replayed (HX_AMG_GRAPH=0 launches it kernel by kernel)
+        self.use_graph = getattr(be, "supports_graphs", False) and os.environ.get("HX_AMG_GRAPH", "1") != "0"
+        self._graph = None
         self.single = precision == "single" and getattr(be, "supports_mixed", False)
         self.wdtype = torch.complex64 if self.single else c128
         self.sell_min_rows = sell_min_rows if getattr(be, "supports_sell", False) else None
@@ -326,6 +332,7 @@ class AMG:
     def set_shift(self, ca, cb, cc, fine_values=None):
         """Form P_l = ca*A_l + cb*B_l + cc*C_l on every level; invert the coarsest."""
         be = self.be
+        self._graph = None                    # the captured cycle points at the previous shift's operators
         for i, L in enumerate(self.levels):
             if i == 0 and fine_values is not None:
                 vals = fine_values
@@ -401,14 +408,41 @@ class AMG:
         self._smooth(L, b, L.x, first_zero=False)
         return L.x
 
+    def _capture(self):
+        """Record one V-cycle (input levels[0].v_w, output the fine-level x buffer) into a CUDA graph."""
+        be, L0 = self.be, self.levels[0]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._cycle(0, L0.v_w)                               # eager pass: lazy buffers exist before capture
+            n0 = be.launch_count()
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(capture_error_mode="thread_local")
+            try:
+                x = self._cycle(0, L0.v_w)
+            finally:
+                g.capture_end()
+            self._graph_kernels = be.launch_count() - n0
+            be.add_launches(-self._graph_kernels)                # recorded, not run
+        cur.wait_stream(side)
+        self._graph, self._graph_x = g, x
+
     def apply(self, v, out):
         """out = V-cycle(v)."""
-        if self.single:
-            L0 = self.levels[0]
+        L0 = self.levels[0]
+        if self.single or self.use_graph:
             if not hasattr(L0, "v_w"):
                 L0.v_w = self.be.zeros(L0.n, dtype=self.wdtype)
-            L0.v_w.copy_(v)                       # complex128 -> complex64
+            L0.v_w.copy_(v)                       # complex128 -> complex64 (or the graph's fixed input)
             v = L0.v_w
+        if self.use_graph and len(self.levels) > 1:
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+            self.be.add_launches(self._graph_kernels)
+            out.copy_(self._graph_x)
+            return out
         x = self._cycle(0, v)
         out.copy_(x)                              # (complex64 ->) complex128
         return out

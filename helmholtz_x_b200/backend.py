@@ -87,6 +87,7 @@ class CudaBackend:
     supports_sell = True
     supports_mixed = True        # complex64 kernels for the multigrid cycle
     supports_spgemm = True       # hx_spgemm_* for the multigrid set-up
+    supports_graphs = True       # CUDA-graph capture of fixed launch sequences (the multigrid cycle)
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():
@@ -232,6 +233,10 @@ class CudaBackend:
 
     def launch_count(self):
         return int(_lib.call("hx_launch_count"))
+
+    def add_launches(self, n):
+        """Account for kernels launched by a CUDA-graph replay (they bypass the C-ABI entry points)."""
+        _lib.load().hx_launch_count_add(int(n))
 
     def reset_launch_count(self):
         _lib.load().hx_launch_count_reset()

@@ -10,3 +10,4 @@ extern "C" const char* hx_last_error(void) { return hx::g_err; }
 extern "C" int hx_version(void) { return 100; }
 extern "C" int64_t hx_launch_count(void) { return hx::g_launches; }
 extern "C" void hx_launch_count_reset(void) { hx::g_launches = 0; }
+extern "C" void hx_launch_count_add(int64_t n) { hx::g_launches += n; }

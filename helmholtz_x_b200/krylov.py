@@ -22,10 +22,17 @@ class ArnoldiBasis:
         self.h1 = be.zeros(m + 2)
         self.h2 = be.zeros(m + 2)
         self._h1r = torch.view_as_real(self.h1)
+        # one GPU: the Hessenberg column comes back through a pinned buffer on a copy stream, so the
+        # caller can queue the next operator application before waiting for it
+        self.pipelined = getattr(be, "name", "") == "cuda" and getattr(be, "supports_graphs", False)
+        if self.pipelined:
+            self._host = torch.empty(m + 2, dtype=c128).pin_memory()
+            self._copy_stream = torch.cuda.Stream(device=be.device)
+            self._ready = torch.cuda.Event()
+            self._done = torch.cuda.Event()
 
-    def orthogonalize(self, j):
-        """CGS2 of self.w against V[0..j]; stores the normalised result in V[j+1].
-        Returns (h[0..j], beta) on the host."""
+    def orthogonalize_begin(self, j):
+        """Queue CGS2 of self.w against V[0..j]; the normalised result goes to V[j+1]."""
         be, V, w, k = self.be, self.V, self.w, j + 1
         be.multi_dot(V, k, w, self.h1)
         be.multi_axpy(V, k, self.h1, w)
@@ -33,9 +40,27 @@ class ArnoldiBasis:
         nrm2 = self._h1r[k]          # real part of h1[k] receives ||w||^2
         be.multi_axpy(V, k, self.h2, w, hacc=self.h1, nrm2=nrm2)
         be.scale_copy(w, V[j + 1], nrm2=nrm2)
-        host = self.h1[:k + 1].cpu().numpy()
+        if self.pipelined:
+            self._ready.record(torch.cuda.current_stream(be.device))
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._ready)
+                self._host[:k + 1].copy_(self.h1[:k + 1], non_blocking=True)
+                self._done.record(self._copy_stream)
+
+    def orthogonalize_end(self, j):
+        """(h[0..j], beta) of the step queued by orthogonalize_begin(j), on the host."""
+        k = j + 1
+        if self.pipelined:
+            self._done.synchronize()
+            host = self._host[:k + 1].numpy().copy()
+        else:
+            host = self.h1[:k + 1].cpu().numpy()
         beta = float(np.sqrt(max(host[k].real, 0.0)))
         return host[:k].copy(), beta
+
+    def orthogonalize(self, j):
+        self.orthogonalize_begin(j)
+        return self.orthogonalize_end(j)
 
 
 def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, basis=None, work=None, zbasis=None):
@@ -74,46 +99,62 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
         else:
             be.scale_copy(b, V[0], alpha=1.0 / beta)
             first = False
+        # Givens QR of the Hessenberg matrix, column by column, in plain Python complex arithmetic
+        # (NumPy scalar operations cost ~1 us each and this loop runs once per iteration)
         H = np.zeros((m + 1, m), complex)
-        g = np.zeros(m + 1, complex)
-        g[0] = beta
-        cs = np.zeros(m, complex)
-        sn = np.zeros(m, complex)
+        g = [0j] * (m + 1)
+        g[0] = complex(beta)
+        cs = [0j] * m
+        sn = [0j] * m
         j_used = 0
-        for j in range(m):
+        def operator(jj):
+            """w = A M^-1 v_jj (queued)."""
             if precond is not None and zbasis is not None:
-                precond(V[j], zbasis[j])
-                apply_A(zbasis[j], w)
+                precond(V[jj], zbasis[jj])
+                apply_A(zbasis[jj], w)
             elif precond is not None:
-                precond(V[j], z)
+                precond(V[jj], z)
                 apply_A(z, w)
             else:
-                apply_A(V[j], w)
-            h, hb = basis.orthogonalize(j)
+                apply_A(V[jj], w)
+
+        queued = False
+        for j in range(m):
+            if not queued:
+                operator(j)
+            basis.orthogonalize_begin(j)
+            queued = getattr(basis, "pipelined", False) and j + 1 < m and total + 2 <= maxiter
+            if queued:
+                # v_{j+1} is complete on the device: start the next operator application while the
+                # host waits for column j and updates the QR (thrown away if column j converges)
+                operator(j + 1)
+            h, hb = basis.orthogonalize_end(j)
             total += 1
-            col = np.zeros(j + 2, complex)
-            col[:j + 1] = h
-            col[j + 1] = hb
+            col = h.tolist()
+            col.append(complex(hb))
             for i in range(j):
-                t = cs[i] * col[i] + sn[i] * col[i + 1]
-                col[i + 1] = -np.conj(sn[i]) * col[i] + cs[i] * col[i + 1]
-                col[i] = t
+                ci, si, u, v = cs[i], sn[i], col[i], col[i + 1]
+                col[i] = ci * u + si * v
+                col[i + 1] = -si.conjugate() * u + ci * v
             a, bb = col[j], col[j + 1]
-            den = np.sqrt(abs(a) ** 2 + abs(bb) ** 2)
+            den = (abs(a) ** 2 + abs(bb) ** 2) ** 0.5
             if den == 0.0:
-                cs[j], sn[j] = 1.0, 0.0
+                cs[j], sn[j] = 1 + 0j, 0j
+            elif a != 0:
+                cs[j] = complex(abs(a) / den)
+                sn[j] = (a / abs(a)) * bb.conjugate() / den
             else:
-                cs[j] = abs(a) / den if a != 0 else 0.0
-                sn[j] = (a / abs(a)) * np.conj(bb) / den if a != 0 else 1.0
+                cs[j], sn[j] = 0j, 1 + 0j
             col[j] = cs[j] * a + sn[j] * bb
-            col[j + 1] = 0.0
-            g[j + 1] = -np.conj(sn[j]) * g[j]
+            col[j + 1] = 0j
+            g[j + 1] = -sn[j].conjugate() * g[j]
             g[j] = cs[j] * g[j]
             H[:j + 2, j] = col
             j_used = j + 1
             rel = abs(g[j + 1]) / bnorm
             if rel <= rtol or total >= maxiter or hb <= 1e-300:
                 break
+        g = np.asarray(g)
         y = np.linalg.solve(np.triu(H[:j_used, :j_used]), g[:j_used])
         # x += M^{-1} (V y)
         yd = be.asarray(-y, dtype=c128)

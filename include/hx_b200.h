@@ -41,6 +41,9 @@ int hx_version(void);
  * (bench.py reports it as gpu_launches) */
 int64_t hx_launch_count(void);
 void hx_launch_count_reset(void);
+/* kernels run by a CUDA-graph replay of captured hx_* launches do not pass through the entry
+ * points; the host adds them here so the counter stays the number of kernels executed */
+void hx_launch_count_add(int64_t n);
 
 /* ------------------------------------------------------------------ K7 / K8
  * PETSc MatMult on AIJ (helmholtz_x/petsc4py_utils.py:86,96; every SLEPc
