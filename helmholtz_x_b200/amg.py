@@ -135,7 +135,7 @@ RHO_MODE = "smoothpower"
 
 class AMG:
     def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=16,
-                 coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=20000, precision="single"):
+                 coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=250000, precision="single"):
         """A, C real-valued, B complex or None -- all on ONE shared fine pattern.
         precision="single": the V-cycle (smoother, residual, transfers) runs in complex64 --
         it is only a preconditioner; GMRES and everything outside stay complex128."""
@@ -351,7 +351,10 @@ class AMG:
                         L.sellp = SellPattern(be, L.pattern.indptr, L.pattern.indices, L.n, L.n)
                         L.sell_vals = be.empty(max(L.sellp.total, 1), dtype=self.wdtype)
                         L.sell_vals64 = be.empty(max(L.sellp.total, 1)) if (self.single and i == 0) else None
-                    L.Mop = SellMatrix(L.sellp, L.sellp.values_from_csr(vals, out=L.sell_vals))
+                    # kernel variant (unroll, min CTAs/SM) measured on B200 (profiles/r1_profile_parts_*.json):
+                    # complex64 sweeps on a million-row level 37.0 us with (4,6) against 43.5 us with (4,4)
+                    L.Mop = SellMatrix(L.sellp, L.sellp.values_from_csr(vals, out=L.sell_vals),
+                                       variant=2 if (self.single and i == 0) else 0)
                     if i == 0:
                         L.M64 = L.Mop if not self.single else SellMatrix(L.sellp, L.sellp.values_from_csr(vals, out=L.sell_vals64))
                 elif self.single:

@@ -59,10 +59,13 @@ multi_dot_kernel(long long n, int k, const double2* __restrict__ V, long long ld
         if ((int)threadIdx.x < kt) partial[(long long)blockIdx.x * k + j0 + threadIdx.x] = s;
     }
     if (last_block_done(&hdr->counter, gridDim.x * gridDim.y)) {
-        for (int j = threadIdx.x; j < k; j += kRedThreads) {
+        // one warp per output: lanes stride over the per-block partials, then a butterfly sum --
+        // a fixed tree, so the result does not depend on which block finished last
+        for (int j = warp; j < k; j += kRedThreads / 32) {
             double2 s = make_double2(0.0, 0.0);
-            for (unsigned int b = 0; b < gridDim.x; ++b) s = cadd(s, partial[(long long)b * k + j]);
-            out[j] = s;
+            for (unsigned int b = lane; b < gridDim.x; b += 32) s = cadd(s, partial[(long long)b * k + j]);
+            s = warp_sum(s);
+            if (lane == 0) out[j] = s;
         }
         if (threadIdx.x == 0) hdr->counter = 0;
     }
@@ -107,10 +110,16 @@ multi_axpy_kernel(long long n, int k, const double2* __restrict__ V, long long l
         partial[blockIdx.x] = s;
     }
     if (last_block_done(&hdr->counter, gridDim.x)) {
+        double s = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += kRedThreads) s += partial[b];
+        s = warp_sum(s);
+        __syncthreads();                       // smn is reused
+        if ((threadIdx.x & 31) == 0) smn[threadIdx.x >> 5] = s;
+        __syncthreads();
         if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += partial[b];
-            *nrm2_out = s;
+            double t = 0.0;
+            for (int wv = 0; wv < kRedThreads / 32; ++wv) t += smn[wv];
+            *nrm2_out = t;
             hdr->counter = 0;
         }
     }
@@ -246,21 +255,29 @@ dense_inverse_kernel(int n, double2* __restrict__ A, int* __restrict__ info, int
 
 // y = A x, A column-major n x n: one warp per 32-row strip would be uncoalesced for
 // column-major, so each thread owns one row and the block walks the columns.
-__global__ void __launch_bounds__(256)
+constexpr int kGemvRows = 32, kGemvParts = 32;
+__global__ void __launch_bounds__(kGemvRows * kGemvParts)
 dense_gemv_kernel(int n, const double2* __restrict__ A, const double2* __restrict__ x, double2* __restrict__ y) {
+    // block = 32 rows x 32 column groups: the column walk of one row is split 32 ways (the matrix is a
+    // few hundred columns wide and the solve sits on the critical path of every multigrid cycle), then
+    // the groups are summed in fixed order
     extern __shared__ double2 xs[];
-    for (int j = threadIdx.x; j < n; j += blockDim.x) xs[j] = x[j];
+    __shared__ double2 part[kGemvParts][kGemvRows + 1];
+    const int tid = threadIdx.y * kGemvRows + threadIdx.x;
+    for (int j = tid; j < n; j += kGemvRows * kGemvParts) xs[j] = x[j];
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double2 a0 = make_double2(0.0, 0.0), a1 = a0;
-    int j = 0;
-    for (; j + 1 < n; j += 2) {
-        cfma(a0, A[i + (long long)j * n], xs[j]);
-        cfma(a1, A[i + (long long)(j + 1) * n], xs[j + 1]);
+    const int i = blockIdx.x * kGemvRows + threadIdx.x;
+    double2 a0 = make_double2(0.0, 0.0);
+    if (i < n)
+        for (int j = threadIdx.y; j < n; j += kGemvParts) cfma(a0, A[i + (long long)j * n], xs[j]);
+    part[threadIdx.y][threadIdx.x] = a0;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < n) {
+        double2 s = make_double2(0.0, 0.0);
+#pragma unroll 8
+        for (int g = 0; g < kGemvParts; ++g) s = cadd(s, part[g][threadIdx.x]);
+        y[i] = s;
     }
-    if (j < n) cfma(a0, A[i + (long long)j * n], xs[j]);
-    y[i] = cadd(a0, a1);
 }
 
 static int red_blocks(long long n) {
@@ -345,7 +362,7 @@ extern "C" int hx_dense_inverse(int n, double* a, int32_t* info_dev, hx_stream_t
 
 extern "C" int hx_dense_gemv(int n, const double* a, const double* x, double* y, hx_stream_t stream) {
     if (n <= 0) return HX_OK;
-    dense_gemv_kernel<<<ceil_div(n, 256), 256, (size_t)n * sizeof(double2), (cudaStream_t)stream>>>(
+    dense_gemv_kernel<<<ceil_div(n, kGemvRows), dim3(kGemvRows, kGemvParts), (size_t)n * sizeof(double2), (cudaStream_t)stream>>>(
         n, (const double2*)a, (const double2*)x, (double2*)y);
     return check_launch("dense_gemv_kernel");
 }

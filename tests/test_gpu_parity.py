@@ -379,16 +379,22 @@ def test_amg_vcycle_matches_host_double_and_gmres_converges():
     assert mats.ops.stats["inner_iterations"] <= 60, mats.ops.stats
 
 
-@pytest.mark.parametrize("precision", ["single", "double"])
-def test_amg_precision_modes_reach_full_accuracy(precision):
-    """The complex64 V-cycle is only a preconditioner: the complex128 GMRES must still reach 1e-11."""
+@pytest.mark.parametrize("precision,sell_min_rows,graph", [("single", 1000, True), ("double", 1000, True),
+                                                           ("single", 10 ** 9, True), ("single", 1000, False)])
+def test_amg_precision_modes_reach_full_accuracy(precision, sell_min_rows, graph, monkeypatch):
+    """The complex64 V-cycle is only a preconditioner: the complex128 GMRES must still reach 1e-11 --
+    with the levels in SELL-32 (what million-row levels use) or CSR, replayed from a CUDA graph or
+    launched kernel by kernel."""
     from helmholtz_x_b200.operators import ShiftedSolver
+    monkeypatch.setenv("HX_AMG_GRAPH", "1" if graph else "0")
     case = cases.annulus()
     mats = gpu_operators(case)
-    mats.ops.amg_options = {"precision": precision}
+    mats.ops.amg_options = {"precision": precision, "sell_min_rows": sell_min_rows}
     s = case.target
     solver = ShiftedSolver(mats.ops, {"A": 1.0, "B": s, "C": s ** 2}, rtol=1e-11)
     assert solver.mg.single == (precision == "single")
+    assert solver.mg.use_graph == graph
+    assert getattr(solver.mg.levels[0].Mop, "is_sell", False) == (sell_min_rows == 1000)
     rng = np.random.default_rng(8)
     n = mats.ops.n
     bvec = be().asarray(rng.standard_normal(n) + 1j * rng.standard_normal(n), dtype=torch.complex128)
