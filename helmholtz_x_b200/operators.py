@@ -220,7 +220,11 @@ class OperatorSet:
         """Global coarse correction of the multi-GPU preconditioner (dist.CoarseCorrection)."""
         if getattr(self, "_coarse", None) is None:
             from .dist import CoarseCorrection
-            self._coarse = CoarseCorrection(self.space, self.base)
+            import os
+            # measured on the 35 k-DoF annulus, 2 ranks (GMRES iterations per solve; one rank: 46):
+            # nc 1000 -> 68, 2000 -> 60; a second (post) coarse correction changes nothing.  The dense
+            # inverse kernel holds nc <= 1400.
+            self._coarse = CoarseCorrection(self.space, self.base, nc=min(int(os.environ.get("HX_DIST_NC", "1000")), 1400))
         return self._coarse
 
     def amg(self):
