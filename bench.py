@@ -277,7 +277,7 @@ def run_b200(args):
                    "step": "pattern + assemble A,B,C + D + fixed-point omega iteration (PEP shift-invert Krylov-Schur)",
                    "dofs": mats_n(g, args.degree), "cells": int(g["cells"].shape[0]),
                    "l2": "roofline loop re-reads a 328 MB matrix (> 126 MB L2) every launch at 1M DoF; spmv_10m uses 3.3 GB",
-                   "ten_million_dof_step": "measured separately (335 s on one B200): profiles/r1_bench_10M_step.json",
+                   "ten_million_dof_step": "measured separately (123 s on one B200): profiles/r1_bench_10M_step_final3.json",
                    "multi_gpu": ("rows partitioned over ranks (Morton chunks), NCCL halo exchange + all-reduced Gram "
                                  "columns, block-Jacobi AMG") if world > 1 else "single"},
         "omega": [float(np.real(omega)), float(np.imag(omega))],
