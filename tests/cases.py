@@ -92,6 +92,22 @@ def rijkeffd():
         target=180 * 2 * np.pi, nev=2, tol=1e-8)
 
 
+def flamedduct():
+    """numerical_examples/Longitudinal/NetworkCode/FlamedDuct/{params,active}.py: choked inlet / outlet
+    (tags 3 / 8), temperature parameter (variable gamma), half-Gaussian heat release, n-tau FTF."""
+    m = mesh("flamedduct")
+    p_gas = 100000.0; r_gas = 287.1; T_passive = 1000.0; T_flame = 1500.0
+    x_f = np.array([[0.0, 0.0, 0.50]]); x_r = np.array([[0.0, 0.0, 0.35]])
+    T = ox.step_field(m, x_f, T_passive, T_flame)
+    return Case(
+        mesh=m, degree=1, bcs={3: {"ChokedInlet": 9.2224960671405849E-003}, 8: {"ChokedOutlet": 1.1408306741423997E-002}},
+        c=T, parameter_is_temperature=True, c_is_dg0=False,
+        flame="distributed", w=ox.gaussian_function(m, x_r, 0.025), h=ox.half_gaussian_function(m, x_f, 0.025),
+        rho=p_gas / (r_gas * T), T=T, gamma=None,
+        q_0=-57015.232012607579, u_b=11.485465769828917, ftf=("ntau", 1, 0.2E-3),
+        target=250 * 2 * np.pi, nev=2, tol=1e-8)
+
+
 def annulus_c(m):
     """fullAnnulus/params.py:53-70: DG0 speed of sound from the cell midpoint z."""
     z = m.x[m.cells].mean(axis=1)[:, 2]
