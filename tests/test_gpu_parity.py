@@ -449,6 +449,15 @@ def test_fpi_rijke3d_config1_matches_golden_log_and_eigenvector():
     assert np.abs(sgn * pm - pg).max() / np.abs(pg).max() < 1e-7
 
 
+def test_fpi_flamedduct_choked_boundaries_match_golden():
+    """.../NetworkCode/FlamedDuct/Results/Active/active.log:21-56: choked inlet / outlet, temperature
+    parameter (variable gamma), half-Gaussian heat release, 33,855 dofs, PEP fixed-point iteration."""
+    case = cases.flamedduct()
+    _, _, E = _run_fpi(case)
+    gold = [cases.cplx(p) for p in G["flamedduct_active_fpi"]["omegas"]]
+    _check_history(E.omega_history, gold, atol=7.1e-9)      # log prints 8 decimals
+
+
 def test_fpi_prf_pep_direct_and_adjoint_match_golden():
     case = cases.prf_rijke3d()
     _, _, E = _run_fpi(case)
