@@ -159,6 +159,55 @@ def spmv_roofline(be, M, launches=200, warmup=50):
     return ms, nbytes
 
 
+def iteration_breakdown(be, ops, peak):
+    """Device time (CUDA events) of the three parts of one preconditioned GMRES iteration on the
+    operators the step just used: multigrid cycle (CUDA-graph replay), operator apply, and one CGS2
+    step against k = 32 basis vectors.  CGS2 bytes: 4 passes over k vectors + 10 n-vector
+    reads/writes of w (two dots, two updates, normalise, and the copy that refills w)."""
+    import torch
+    n = ops.n
+    mg, st = ops.amg(), ops._shift_state
+    gen = torch.Generator(be.device).manual_seed(1)
+    b = torch.randn(n, dtype=torch.float64, device=be.device, generator=gen).to(torch.complex128)
+    y = be.zeros(n)
+    cur = torch.cuda.current_stream()
+
+    def timed(fn, reps):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(cur)
+        for _ in range(reps):
+            fn()
+        e1.record(cur)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    t_cycle = timed(lambda: mg.apply(b, y), 50)
+    t_apply = timed(lambda: be.spmv(st["Pop"], b, y), 50)
+    basis = st["basis"]
+    k = min(32, basis.m - 1)
+    for j in range(k + 1):
+        basis.V[j].copy_(torch.randn(n, dtype=torch.float64, device=be.device, generator=gen).to(torch.complex128))
+        basis.V[j].mul_(1.0 / float(n) ** 0.5)
+
+    def cgs2():
+        basis.w.copy_(b)
+        basis.orthogonalize_begin(k - 1)
+
+    t_cgs = timed(cgs2, 20)
+    nbytes = (64.0 * k + 160.0) * n
+    gbs = nbytes / (t_cgs * 1e-6) / 1e9
+    total = t_cycle + t_apply + t_cgs
+    return {"multigrid_cycle_us": round(t_cycle, 1), "operator_apply_us": round(t_apply, 1),
+            "cgs2_k32_us": round(t_cgs, 1), "share": {"multigrid_cycle": round(t_cycle / total, 3),
+                                                      "operator_apply": round(t_apply / total, 3),
+                                                      "cgs2": round(t_cgs / total, 3)},
+            "cgs2_kernels": "multi_dot_kernel x2, multi_axpy_kernel x2, scale_copy_kernel",
+            "cgs2_bytes": nbytes, "cgs2_gbs": round(gbs, 1), "cgs2_frac_of_peak": round(gbs / peak, 4),
+            "amg_levels": mg.sizes, "k": k}
+
+
 def run_b200(args):
     import contextlib
     import io
@@ -242,6 +291,12 @@ def run_b200(args):
             "traffic": 318.4e6 if (csr.n_rows == 998400 and world == 1) else None, "bytes_per_launch": nbytes,
             "ms_per_launch": round(ms, 5), "n": csr.n_rows, "nnz": csr.nnz, "model": "20*nnz + 36*n bytes (SURVEY 8d)",
             "csr_vector_gbs": round(nbytes / (ms_csr * 1e-3) / 1e9, 1)}
+    parts = None
+    if world == 1:
+        try:
+            parts = iteration_breakdown(be, mats.ops, peak)
+        except Exception as ex:              # noqa: BLE001
+            parts = {"error": str(ex)[:300]}
     big = None
     if args.spmv_dofs and rank == 0 and world == 1:
         try:
@@ -283,7 +338,7 @@ def run_b200(args):
         "omega": [float(np.real(omega)), float(np.imag(omega))],
         "e2e": {"value": round(e2e_s, 4), "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "solver_stats": stats,
-        "roofline": roof, "spmv_10m": big, "clocks": clocks,
+        "roofline": roof, "iteration": parts, "spmv_10m": big, "clocks": clocks,
     }
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
