@@ -241,3 +241,27 @@ def test_bloch_reduction_host_logic():
     assert abs(omega - cases.cplx(G["bloch_active_fpi"]["final"])) < 2e-6
     with pytest.raises(NotImplementedError):
         eigensolvers.eps_solver(bl.A, bl.C, case.passive_target, nev=2, two_sided=True)
+
+
+def test_bloch_reduction_p2_geometric_pairing():
+    """P2 on the sector: master/slave edge dofs are paired as rotation images as well, and the reduced
+    operators equal the oracle's NB*M*BN."""
+    from helmholtz_x_b200.bloch_operator import Blochifier
+    case = cases.bloch()
+    case["degree"] = 2
+    hops = HostOperators(case)
+    sp_ = hops.oracle.space
+    bl = Blochifier(case.mesh, case.bcs, case.N, hops)
+    md, sd = ox.bloch_pairs(sp_, case.master, case.slave, case.N, pairing="geometric")
+    assert len(md) > 311 and np.array_equal(bl.dofs_master, md) and np.array_equal(bl.dofs_slave, sd)
+    X = sp_.dof_x
+    a = 2 * np.pi / case.N
+    Rm = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    d = min(np.abs(X[md] @ Rm.T - X[sd]).max(), np.abs(X[md] @ Rm - X[sd]).max())
+    assert d < 1e-9
+    BN, NB = ox.bloch_maps(sp_.n, md, sd, case.N)
+    for name, M in (("A", hops.oracle.A), ("B", hops.oracle.B), ("C", hops.oracle.C)):
+        want = ox.blochify(M, BN, NB)
+        got = getattr(bl, name).to_scipy()
+        assert abs(got - want).max() <= 1e-13 * abs(want).max(), name
+    assert abs(want - want.conj().T).max() <= 1e-13 * abs(want).max()       # C_b Hermitian
