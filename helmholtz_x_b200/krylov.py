@@ -31,14 +31,18 @@ class ArnoldiBasis:
             self._ready = torch.cuda.Event()
             self._done = torch.cuda.Event()
 
-    def orthogonalize_begin(self, j):
-        """Queue CGS2 of self.w against V[0..j]; the normalised result goes to V[j+1]."""
+    def orthogonalize_begin(self, j, passes=2):
+        """Queue classical Gram-Schmidt of self.w against V[0..j] (passes=2: with re-orthogonalisation,
+        CGS2); the normalised result goes to V[j+1]."""
         be, V, w, k = self.be, self.V, self.w, j + 1
-        be.multi_dot(V, k, w, self.h1)
-        be.multi_axpy(V, k, self.h1, w)
-        be.multi_dot(V, k, w, self.h2)
         nrm2 = self._h1r[k]          # real part of h1[k] receives ||w||^2
-        be.multi_axpy(V, k, self.h2, w, hacc=self.h1, nrm2=nrm2)
+        be.multi_dot(V, k, w, self.h1)
+        if passes == 1:
+            be.multi_axpy(V, k, self.h1, w, nrm2=nrm2)
+        else:
+            be.multi_axpy(V, k, self.h1, w)
+            be.multi_dot(V, k, w, self.h2)
+            be.multi_axpy(V, k, self.h2, w, hacc=self.h1, nrm2=nrm2)
         be.scale_copy(w, V[j + 1], nrm2=nrm2)
         if self.pipelined:
             self._ready.record(torch.cuda.current_stream(be.device))
@@ -63,7 +67,8 @@ class ArnoldiBasis:
         return self.orthogonalize_end(j)
 
 
-def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, basis=None, work=None, zbasis=None):
+def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, basis=None, work=None, zbasis=None,
+          orth_passes=2):
     """Right-preconditioned restarted GMRES: solves A x = b, x overwritten (start 0).
     apply_A(v, out), precond(v, out).  Returns (iterations, relative residual).
     zbasis (restart x n): flexible GMRES -- the preconditioned vectors z_j = M^-1 v_j are kept
@@ -85,6 +90,8 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
     total = 0
     rel = 1.0
     first = True
+    estimate_converged = False
+    last_true = np.inf
     while total < maxiter:
         if not first:
             # true residual r = b - A x
@@ -95,6 +102,12 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
             rel = beta / bnorm
             if rel <= rtol:
                 break
+            if estimate_converged:
+                # the recurrence says converged, the recomputed residual does not: refine with further
+                # cycles while they still help (near-singular shifts floor above rtol)
+                if rel > 0.5 * last_true:
+                    break
+                last_true = rel
             be.scale_copy(w, V[0], alpha=1.0 / beta)
         else:
             be.scale_copy(b, V[0], alpha=1.0 / beta)
@@ -122,7 +135,7 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
         for j in range(m):
             if not queued:
                 operator(j)
-            basis.orthogonalize_begin(j)
+            basis.orthogonalize_begin(j, orth_passes)
             queued = getattr(basis, "pipelined", False) and j + 1 < m and total + 2 <= maxiter
             if queued:
                 # v_{j+1} is complete on the device: start the next operator application while the
@@ -152,7 +165,10 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
             H[:j + 2, j] = col
             j_used = j + 1
             rel = abs(g[j + 1]) / bnorm
-            if rel <= rtol or total >= maxiter or hb <= 1e-300:
+            if rel <= 0.9 * rtol or hb <= 1e-300:
+                estimate_converged = True
+                break
+            if total >= maxiter:
                 break
         g = np.asarray(g)
         y = np.linalg.solve(np.triu(H[:j_used, :j_used]), g[:j_used])
@@ -168,8 +184,10 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
                 be.axpby(1.0, z, 1.0, x)
             else:
                 be.axpby(1.0, w, 1.0, x)
-        if rel <= rtol:
+        if total >= maxiter:
             break
+        # the loop head recomputes the true residual b - A x and stops there: the recurrence estimate
+        # is not trusted (single-pass Gram-Schmidt, complex64 preconditioner)
     return total, rel
 
 

@@ -265,3 +265,35 @@ def test_bloch_reduction_p2_geometric_pairing():
         got = getattr(bl, name).to_scipy()
         assert abs(got - want).max() <= 1e-13 * abs(want).max(), name
     assert abs(want - want.conj().T).max() <= 1e-13 * abs(want).max()       # C_b Hermitian
+
+
+def test_single_pass_gram_schmidt_and_verified_residual(rijke, monkeypatch):
+    """Inner GMRES: one Gram-Schmidt pass per step (the default) against two -- same iteration counts,
+    true residual below rtol; a shift next to an eigenvalue floors above rtol and must return at the
+    floor instead of spinning to maxiter."""
+    import helmholtz_x_b200.operators as O
+    case, hops = rijke
+    ops = hops.ops
+    s2 = case.target ** 2
+    rng = np.random.default_rng(11)
+    b = torch.from_numpy(rng.standard_normal(ops.n) + 1j * rng.standard_normal(ops.n))
+    counts = {}
+    for passes in (2, 1):
+        monkeypatch.setattr(O, "GMRES_ORTH_PASSES", passes)
+        ops._shift_state = None
+        solver = O.ShiftedSolver(ops, {"A": 1.0, "C": s2})
+        x = torch.zeros_like(b)
+        i0 = ops.stats["inner_iterations"]
+        solver.solve(b, x)
+        counts[passes] = ops.stats["inner_iterations"] - i0
+        P = solver.P.to_scipy()
+        assert np.linalg.norm(P @ x.numpy() - b.numpy()) / np.linalg.norm(b.numpy()) < 1.05e-11
+    assert abs(counts[1] - counts[2]) <= 2, counts
+    # the second solve of this eigen-solve floors at ~5e-11 (> rtol): it must return there after a short
+    # refinement cycle (34 iterations), not run to maxiter = 512
+    monkeypatch.setattr(O, "GMRES_ORTH_PASSES", 1)
+    ops._shift_state = None
+    i0, s0 = ops.stats["inner_iterations"], ops.stats["inner_solves"]
+    eigensolvers.eps_solver(hops.A, hops.C, case.target, nev=2)
+    n_solves = ops.stats["inner_solves"] - s0
+    assert ops.stats["inner_iterations"] - i0 < 40 * n_solves, ops.stats
