@@ -51,3 +51,15 @@ def test_host_colouring_is_valid():
     for c in range(nc):
         nodes = cells[color == c].ravel()
         assert len(np.unique(nodes)) == len(nodes), "two cells of one colour share a vertex"
+
+
+def test_every_entry_point_is_documented_in_integration_md():
+    """INTEGRATION.md maps each C entry point to the reference call site it replaces."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "hx_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = set(re.findall(r"\b(hx_[A-Za-z0-9_]+)\s*\(", hdr))
+    prefixes = [p[:-1] for p in re.findall(r"`(hx_[a-z0-9_]+\*)`", doc)]
+    missing = [s for s in sorted(syms) if s not in doc and not any(s.startswith(p) for p in prefixes)]
+    assert not missing, missing
