@@ -7,6 +7,8 @@ fixed-point / Newton recurrences, rank partitioning) can be exercised by the
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -18,6 +20,9 @@ f64 = torch.float64
 class HostBackend:
     name = "host-test-double"
     supports_sell = False
+    # HX_HOST_MIXED=1: run the multigrid cycle in complex64 as the CUDA backend does (the NumPy/SciPy
+    # calls below follow the dtype of their operands), to exercise flexible GMRES on the CPU
+    supports_mixed = os.environ.get("HX_HOST_MIXED", "0") == "1"
 
     def __init__(self):
         self.device = torch.device("cpu")
