@@ -9,18 +9,19 @@ Set-up (once per mesh; sigma-independent):
   * tentative prolongator T (piecewise constant, normalised), smoothed with one damped
     Jacobi step on the SPD surrogate K = -A + tau C:  P = (I - 4/(3 rho) D^-1 K) T;
   * Galerkin coarse operators A_c = P^T A P, B_c, C_c on a common coarse pattern.
-  The sparse products of the set-up go through torch.sparse (cuSPARSE SpGEMM): library
-  plumbing outside the per-iteration path.
+  The sparse products of the set-up run through the library's own SpGEMM kernels (spgemm.py) on
+  levels of >= 20 k rows; small / dense coarse levels and the CPU test double use torch.sparse.
 Per shift (every outer fixed-point / Newton step): one `combine_abc` kernel per level
 forms P_l(sigma) on that level's pattern, one Gauss-Jordan kernel inverts the coarsest.
-Per application: V(nu,nu) cycle of damped-Jacobi sweeps, CSR SpMVs for restriction /
-prolongation and a dense GEMV on the coarsest level -- all libhx_b200 kernels.
+Per application: V(nu,nu) cycle of damped-Jacobi sweeps (SELL-32 on levels >= 250 k rows, CSR-vector
+below), CSR SpMVs for restriction / prolongation and a dense GEMV on the coarsest level -- all
+libhx_b200 kernels, in complex64 by default, captured once per shift in a CUDA graph and replayed.
 """
 from __future__ import annotations
 
-import numpy as np
 import os
 
+import numpy as np
 import torch
 
 from .backend import CsrMatrix
