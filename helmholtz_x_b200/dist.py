@@ -342,3 +342,133 @@ class CoarseCorrection:
         be.dense_gemv(self.inv, self.t, self.y)
         be.spmv(self.P0, self.y, x)
         return x
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-distributed multigrid cycle (HX_DIST_HIERARCHY=1; default off until measured on GPUs).
+#
+# The two-level Schwarz preconditioner above loses the couplings across ranks on every level
+# and needs 1.5-1.8x the iterations of the single-GPU hierarchy.  Here every rank builds the
+# *same* global hierarchy once per mesh (replicated set-up: the assembled rows are all-gathered,
+# 32 B per nonzero), the fine level -- where the bytes are -- is smoothed on the owned rows with
+# one halo exchange per sweep, the restricted residual is all-reduced, and the levels below run
+# replicated.  The cycle is then the single-GPU cycle up to summation order, so the iteration
+# count does not depend on the number of ranks.
+# ---------------------------------------------------------------------------------------------
+def _all_gather_rows(t, world):
+    """Concatenation over ranks of a 1-D/2-D tensor whose first dimension differs per rank."""
+    if world == 1:
+        return t
+    cplx = t.is_complex()
+    src = torch.view_as_real(t.contiguous()) if cplx else t.contiguous()
+    n = torch.tensor([src.shape[0]], dtype=torch.int64, device=src.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c) for c in counts]
+    pad = torch.zeros((max(counts),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    pad[:src.shape[0]] = src
+    bufs = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    out = torch.cat([b[:c] for b, c in zip(bufs, counts)])
+    return torch.view_as_complex(out) if cplx else out
+
+
+def _csr_rows(M: CsrMatrix, rows):
+    """Sub-matrix of the given rows (all columns)."""
+    ip = M.indptr.long()
+    cnt = (ip[1:] - ip[:-1])[rows]
+    ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=rows.device)
+    ptr[1:] = torch.cumsum(cnt, 0)
+    total = int(ptr[-1])
+    idx = torch.repeat_interleave(ip[rows] - ptr[:-1], cnt, output_size=total) + torch.arange(total, device=rows.device)
+    return CsrMatrix(int(rows.numel()), M.n_cols, ptr.to(torch.int32).contiguous(), M.indices[idx].contiguous(),
+                     M.values[idx].contiguous())
+
+
+def _csr_transpose(M: CsrMatrix):
+    ip = M.indptr.long()
+    rows = torch.repeat_interleave(torch.arange(M.n_rows, device=ip.device), ip[1:] - ip[:-1], output_size=M.nnz)
+    cols = M.indices.long()
+    order = torch.sort(cols * M.n_rows + rows).indices
+    ptr = torch.zeros(M.n_cols + 1, dtype=torch.int64, device=ip.device)
+    ptr[1:] = torch.cumsum(torch.bincount(cols, minlength=M.n_cols), 0)
+    return CsrMatrix(M.n_cols, M.n_rows, ptr.to(torch.int32).contiguous(), rows[order].to(torch.int32).contiguous(),
+                     M.values[order].contiguous())
+
+
+class DistHierarchy:
+    def __init__(self, space: "DistSpace", base, **amg_options):
+        from .amg import AMG
+        part, be = space.part, space.local_be
+        self.part, self.be, self.space = part, be, space
+        world = part.world
+        ip, ix = space._pattern
+        dev = ip.device
+        n_own, ng = part.n_own, part.n_global
+        l2g = torch.as_tensor(part.l2g, device=dev)
+        rows_loc = torch.repeat_interleave(torch.arange(n_own, device=dev), (ip[1:] - ip[:-1]).long())
+        key = _all_gather_rows(l2g[rows_loc] * ng + l2g[ix.long()], world)
+        order = torch.sort(key).indices
+        key = key[order]
+        grow = torch.div(key, ng, rounding_mode="floor")
+        gptr = torch.zeros(ng + 1, dtype=torch.int64, device=dev)
+        gptr[1:] = torch.cumsum(torch.bincount(grow, minlength=ng), 0)
+        gptr, gidx = gptr.to(torch.int32).contiguous(), (key - grow * ng).to(torch.int32).contiguous()
+
+        def glob(v):
+            return CsrMatrix(ng, ng, gptr, gidx, _all_gather_rows(v, world)[order].contiguous())
+        coords = torch.zeros(ng, 3, dtype=space.dof_coords.dtype, device=dev)
+        coords[_all_gather_rows(l2g[:n_own], world)] = _all_gather_rows(space.dof_coords, world)
+        B = glob(base["B"]) if base.get("B") is not None else None
+        self.mg = AMG(be, glob(base["A"]), glob(base["C"]), B, coords, **amg_options)
+        self.mg.use_graph = False
+        mg = self.mg
+        self.single, self.wdtype, self.nu, self.omega = mg.single, mg.wdtype, mg.nu, mg.omega
+        if len(mg.levels) < 2:
+            raise ValueError("the distributed cycle needs at least two levels")
+        own = l2g[:n_own]
+        self.P_own = _csr_rows(mg.levels[0].P, own)                     # n_own x n_1 (global coarse columns)
+        self.R_own = _csr_transpose(self.P_own)                         # n_1 x n_own
+        wd = self.wdtype
+        self.b = be.zeros(n_own, dtype=wd)
+        self.r = be.zeros(n_own, dtype=wd)
+        self.xa = be.zeros(part.n_loc, dtype=wd)
+        self.xb = be.zeros(part.n_loc, dtype=wd)
+        self.dinv = be.zeros(n_own)
+        self.M = None
+
+    def set_fine(self, values_own):
+        """values_own: P(sigma) on the owned rows (space.pattern(), complex128), after mg.set_shift."""
+        ip, ix = self.space._pattern
+        M = CsrMatrix(self.part.n_own, self.part.n_loc, ip, ix, values_own)
+        self.be.diag_inv(M, self.dinv)
+        self.dinv_w = self.dinv.to(self.wdtype) if self.single else self.dinv
+        self.M = M.with_values(values_own.to(self.wdtype)) if self.single else M
+
+    def _sweeps(self, count, first_zero):
+        be, part, M = self.be, self.part, self.M
+        if first_zero:
+            be.jacobi_sweep(M, self.dinv_w, self.b, None, self.xa, self.omega)
+            count -= 1
+        for _ in range(count):
+            part.exchange(self.xa)
+            be.jacobi_sweep(M, self.dinv_w, self.b, self.xa, self.xb, self.omega)
+            self.xa, self.xb = self.xb, self.xa
+
+    def apply(self, v, out):
+        """out = V-cycle(v) on the owned entries: fine level distributed, levels >= 1 replicated."""
+        be, part, mg = self.be, self.part, self.mg
+        n_own = part.n_own
+        self.b.copy_(v)
+        self._sweeps(self.nu, first_zero=True)
+        part.exchange(self.xa)
+        be.spmv(self.M, self.xa, self.r, alpha=-1.0, beta=1.0, y0=self.b)           # r = b - M x
+        b1 = mg.levels[1].b_
+        be.spmv(self.R_own, self.r, b1)
+        if part.world > 1:
+            dist.all_reduce(torch.view_as_real(b1))
+        x1 = mg._cycle(1, b1)
+        be.spmv(self.P_own, x1, self.xa, alpha=1.0, beta=1.0, y0=self.xa)           # owned part of x += P x1
+        self._sweeps(self.nu, first_zero=False)
+        out.copy_(self.xa[:n_own])
+        return out

@@ -234,7 +234,24 @@ class OperatorSet:
             self._coarse = CoarseCorrection(self.space, self.base, nc=min(int(os.environ.get("HX_DIST_NC", "1000")), 1400))
         return self._coarse
 
+    def hierarchy(self):
+        """Row-distributed multigrid cycle (dist.DistHierarchy), HX_DIST_HIERARCHY=1; None otherwise."""
+        import os
+        if self.part is None or os.environ.get("HX_DIST_HIERARCHY", "0") != "1":
+            return None
+        if getattr(self, "_hier", None) is None:
+            import time
+            from .dist import DistHierarchy
+            t0 = time.perf_counter()
+            self._hier = DistHierarchy(self.space, self.base, **self.amg_options)
+            self._amg = self._hier.mg
+            self.stats["amg_setups"] += 1
+            self.stats["t_amg_setup"] += time.perf_counter() - t0
+        return self._hier
+
     def amg(self):
+        if self._amg is None and self.hierarchy() is not None:
+            return self._amg
         if self._amg is None and self.part is not None:
             # block-Jacobi across GPUs: each rank's hierarchy lives on its diagonal block
             import time
@@ -268,7 +285,8 @@ class ShiftedSolver:
 
     def __init__(self, ops: OperatorSet, terms, lowrank=(), rtol=1e-11, restart=64, maxiter=512, transposed=False):
         import time
-        if ops.part is not None:
+        hier = ops.hierarchy()
+        if ops.part is not None and hier is None:
             restart, maxiter = 80, 800          # the two-level Schwarz preconditioner needs more iterations
         self.ops, self.be = ops, ops.be
         be = self.be
@@ -282,7 +300,10 @@ class ShiftedSolver:
             use_bh = t.get("Bh", 0) != 0
             P_values = ops.combine(t)
             P = ops.space.matrix(P_values)
-            fine_vals = P_values if ops.part is None else P_values[ops.space.diag_sel].contiguous()
+            if hier is not None:
+                fine_vals = None                 # replicated global levels are combined from their own bases
+            else:
+                fine_vals = P_values if ops.part is None else P_values[ops.space.diag_sel].contiguous()
             if use_bh:
                 # coarse B^H = conj(B_c): run the hierarchy on conjugated B
                 for L in mg.levels:
@@ -299,7 +320,9 @@ class ShiftedSolver:
             else:
                 mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=fine_vals)
             Pop = mg.fine_operator() if (len(mg.levels) > 1 and ops.part is None) else P
-            if ops.part is not None:
+            if hier is not None:
+                hier.set_fine(P_values)
+            elif ops.part is not None:
                 ops.coarse().set_shift(t)
             st = {"key": key, "P_values": P_values, "P": P, "Pop": Pop, "wood": {},
                   "basis": krylov.ArnoldiBasis(be, ops.n, restart), "work": be.zeros(ops.n),
@@ -326,6 +349,8 @@ class ShiftedSolver:
         AMG cycle on the updated residual (two-level multiplicative Schwarz)."""
         if self.ops.part is None:
             return self.mg.apply(v, out)
+        if self.ops.hierarchy() is not None:
+            return self.ops.hierarchy().apply(v, out)
         cc = self.ops.coarse()
         be = self.be
         xc, r = self.st["xc"], self.st["r"]

@@ -115,10 +115,12 @@ class HostBackend:
 
     def jacobi_sweep(self, M, dinv, b, xin, xout, omega):
         if xin is None:
-            xout.copy_(omega * dinv * b)
+            n = b.numel()
+            xout[:n] = omega * dinv[:n] * b
         else:
-            r = b.numpy() - self._sp(M) @ xin.numpy()
-            xout.copy_(xin + omega * dinv * torch.from_numpy(r))
+            n = M.n_rows                          # rectangular (owned rows x owned+ghost columns) allowed
+            r = b.numpy()[:n] - self._sp(M) @ xin.numpy()[:M.n_cols]
+            xout[:n] = xin[:n] + omega * dinv[:n] * torch.from_numpy(r)
         self.launches += 1
         return xout
 

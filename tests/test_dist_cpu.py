@@ -65,10 +65,11 @@ def _sub_values(part, Mglob, pattern):
     return out
 
 
-def _synthetic_worker(rank, world, port, q):
+def _synthetic_worker(rank, world, port, q, hierarchy=False):
     """Structured synthetic annulus, file-order ('input') partition = z-slabs: SpMV + PEP solve."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["HX_DIST_HIERARCHY"] = "1" if hierarchy else "0"
     _single_thread()
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -94,7 +95,21 @@ def _synthetic_worker(rank, world, port, q):
         E = eigensolvers.pep_solver(A, B, C, target, nev=2)
         Eo = ox.pep_solve(ops_o.A, ops_o.B, ops_o.C, target, 2)
         assert abs(E.getEigenpair(0) - Eo.eigenvalues[0]) / abs(Eo.eigenvalues[0]) < 1e-8
-        q.put((rank, "ok", ops.stats["inner_iterations"]))
+        single = None
+        if hierarchy:
+            # the same eigen-solve on one rank: the row-distributed cycle is the single-rank cycle up to
+            # summation order, so the inner iteration counts must agree
+            assert ops.hierarchy() is not None and ops.amg() is ops.hierarchy().mg
+            from tests.host_helpers import HostSpace
+            V1 = HostSpace(ops_o.space, HostBackend())
+            ops1 = OperatorSet(V1, torch.from_numpy(ox._on_pattern(ops_o.space, ops_o.A).real.copy()),
+                               torch.from_numpy(ox._on_pattern(ops_o.space, ops_o.C).real.copy()),
+                               torch.from_numpy(ox._on_pattern(ops_o.space, ops_o.B)))
+            E1 = eigensolvers.pep_solver(Mat(ops1, {"A": 1.0}), Mat(ops1, {"B": 1.0}), Mat(ops1, {"C": 1.0}), target, nev=2)
+            assert abs(E1.getEigenpair(0) - E.getEigenpair(0)) / abs(E.getEigenpair(0)) < 1e-9
+            single = ops1.stats["inner_iterations"]
+            assert abs(ops.stats["inner_iterations"] - single) <= 0.05 * single + 2, (ops.stats, ops1.stats)
+        q.put((rank, "ok", (ops.stats["inner_iterations"], single)))
     except Exception:      # noqa: BLE001
         import traceback
         q.put((rank, "fail", traceback.format_exc()))
@@ -201,14 +216,18 @@ def test_two_rank_partitioned_solve_matches_goldens(ordering):
         p.join(timeout=60)
     for rank, status, info in res:
         assert status == "ok", f"rank {rank}: {info}"
+    print("inner iterations (distributed, single rank):", [info for _, _, info in res])
     print("inner GMRES iterations per rank:", [info for _, _, info in res])
 
 
-def test_two_rank_slab_partition_of_structured_annulus():
+@pytest.mark.parametrize("hierarchy", [False, True])
+def test_two_rank_slab_partition_of_structured_annulus(hierarchy):
+    """hierarchy=False: two-level Schwarz (default).  True: the row-distributed multigrid cycle
+    (HX_DIST_HIERARCHY=1) -- same iteration count as one rank."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_synthetic_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_synthetic_worker, args=(r, 2, port, q, hierarchy)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -216,3 +235,4 @@ def test_two_rank_slab_partition_of_structured_annulus():
         p.join(timeout=60)
     for rank, status, info in res:
         assert status == "ok", f"rank {rank}: {info}"
+    print("inner iterations (distributed, single rank):", [info for _, _, info in res])
