@@ -136,11 +136,19 @@ RHO_MODE = "smoothpower"
 
 class AMG:
     def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=16,
-                 coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=250000, precision="single"):
+                 coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=250000, precision="single",
+                 w_from=None):
         """A, C real-valued, B complex or None -- all on ONE shared fine pattern.
         precision="single": the V-cycle (smoother, residual, transfers) runs in complex64 --
         it is only a preconditioner; GMRES and everything outside stay complex128."""
         self.be, self.nu, self.omega = be, nu, omega
+        # W-cycle: levels >= w_from are visited twice per visit of their parent (None: V-cycle).  Measured
+        # on the CPU double (GMRES iterations per solve, synthetic annulus): 250 k DoF V 37, W from level 1
+        # 29, W from level 2 33; the V-cycle count grows with the number of levels, the W-cycle count
+        # hardly does.  Off by default until timed on the GPU (HX_AMG_WCYCLE=<level>).
+        if w_from is None and os.environ.get("HX_AMG_WCYCLE"):
+            w_from = int(os.environ["HX_AMG_WCYCLE"])
+        self.w_from = w_from
         self.native_min_rows = 20000
         # the V-cycle is a fixed sequence of ~25 small launches on fixed buffers: captured once per
         # shift in a CUDA graph and replayed (HX_AMG_GRAPH=0 launches it kernel by kernel)
@@ -264,6 +272,8 @@ class AMG:
         for L in self.levels:
             L.x = be.zeros(L.n, dtype=wd); L.b_ = be.zeros(L.n, dtype=wd)
             L.r = be.zeros(L.n, dtype=wd); L.t = be.zeros(L.n, dtype=wd)
+            if self.w_from is not None:
+                L.xs = be.zeros(L.n, dtype=wd); L.bs = be.zeros(L.n, dtype=wd)
             L.M = None
             L.Mop = None
             L.sellp = None
@@ -408,6 +418,13 @@ class AMG:
         Lc = self.levels[i + 1]
         be.spmv(L.R, L.r, Lc.b_)
         xc = self._cycle(i + 1, Lc.b_)
+        if self.w_from is not None and self.w_from <= i + 1 < len(self.levels) - 1:
+            # second visit: the cycle applied to the coarse residual corrects xc
+            Lc.xs.copy_(xc)
+            Lc.bs.copy_(Lc.b_)
+            be.spmv(Lc.Mop, Lc.xs, Lc.b_, alpha=-1.0, beta=1.0, y0=Lc.bs)
+            xc = self._cycle(i + 1, Lc.b_)
+            xc.add_(Lc.xs)
         be.spmv(L.P, xc, L.x, alpha=1.0, beta=1.0, y0=L.x)             # x += P xc
         self._smooth(L, b, L.x, first_zero=False)
         return L.x

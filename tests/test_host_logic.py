@@ -316,3 +316,25 @@ def test_flexible_gmres_with_complex64_cycle_on_the_cpu_double(monkeypatch):
     P = solver.P.to_scipy()
     assert np.linalg.norm(P @ x.numpy() - b.numpy()) / np.linalg.norm(b.numpy()) < 1.05e-11
     assert hops.ops.stats["inner_iterations"] < 45
+
+
+def test_w_cycle_option_reduces_iterations_and_keeps_the_solution():
+    """AMG(w_from=1): levels >= 1 visited twice.  Same solution, fewer GMRES iterations (the option is
+    off by default until it is timed on the GPU)."""
+    from helmholtz_x_b200.operators import ShiftedSolver
+    case = cases.annulus()
+    rng = np.random.default_rng(21)
+    its, sols = {}, {}
+    for w_from in (None, 1):
+        hops = HostOperators(case)
+        hops.ops.amg_options = {"w_from": w_from}
+        s = case.target
+        solver = ShiftedSolver(hops.ops, {"A": 1.0, "B": s, "C": s ** 2})
+        assert len(solver.mg.levels) >= 3 and solver.mg.w_from == w_from
+        if w_from is None:
+            b = torch.from_numpy(rng.standard_normal(hops.ops.n) + 1j * rng.standard_normal(hops.ops.n))
+        x = torch.zeros_like(b)
+        solver.solve(b, x)
+        its[w_from], sols[w_from] = hops.ops.stats["inner_iterations"], x.numpy().copy()
+    assert its[1] < its[None], its
+    assert np.linalg.norm(sols[1] - sols[None]) / np.linalg.norm(sols[None]) < 1e-9
