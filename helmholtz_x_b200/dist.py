@@ -423,7 +423,9 @@ class DistHierarchy:
         self.mg = AMG(be, glob(base["A"]), glob(base["C"]), B, coords, **amg_options)
         self.mg.use_graph = False
         mg = self.mg
-        self.single, self.wdtype, self.nu, self.omega = mg.single, mg.wdtype, mg.nu, mg.omega
+        self.single, self.wdtype, self.nu, self.omegas = mg.single, mg.wdtype, mg.nu, mg.omegas
+        if mg.smoother != "jacobi":
+            raise NotImplementedError("the distributed cycle uses constant damping on the fine level")
         if len(mg.levels) < 2:
             raise ValueError("the distributed cycle needs at least two levels")
         own = l2g[:n_own]
@@ -447,12 +449,13 @@ class DistHierarchy:
 
     def _sweeps(self, count, first_zero):
         be, part, M = self.be, self.part, self.M
+        k = 0
         if first_zero:
-            be.jacobi_sweep(M, self.dinv_w, self.b, None, self.xa, self.omega)
-            count -= 1
-        for _ in range(count):
+            be.jacobi_sweep(M, self.dinv_w, self.b, None, self.xa, self.omegas[0])
+            k = 1
+        for s in range(k, count):
             part.exchange(self.xa)
-            be.jacobi_sweep(M, self.dinv_w, self.b, self.xa, self.xb, self.omega)
+            be.jacobi_sweep(M, self.dinv_w, self.b, self.xa, self.xb, self.omegas[s])
             self.xa, self.xb = self.xb, self.xa
 
     def apply(self, v, out):

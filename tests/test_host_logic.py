@@ -338,3 +338,29 @@ def test_w_cycle_option_reduces_iterations_and_keeps_the_solution():
         its[w_from], sols[w_from] = hops.ops.stats["inner_iterations"], x.numpy().copy()
     assert its[1] < its[None], its
     assert np.linalg.norm(sols[1] - sols[None]) / np.linalg.norm(sols[None]) < 1e-9
+
+
+def test_chebyshev_damping_option(rijke):
+    """AMG(smoother="chebyshev"): per-level, per-shift estimate of rho(D^-1 P_l) and the Chebyshev roots
+    as damping factors of the nu sweeps -- same sweeps, fewer iterations, same solution."""
+    from helmholtz_x_b200.operators import ShiftedSolver
+    case, _ = rijke
+    rng = np.random.default_rng(22)
+    out = {}
+    for sm in ("jacobi", "chebyshev"):
+        hops = HostOperators(case)
+        hops.ops.amg_options = {"smoother": sm}
+        solver = ShiftedSolver(hops.ops, {"A": 1.0, "C": case.target ** 2})
+        if sm == "jacobi":
+            b = torch.from_numpy(rng.standard_normal(hops.ops.n) + 1j * rng.standard_normal(hops.ops.n))
+        x = torch.zeros_like(b)
+        solver.solve(b, x)
+        out[sm] = (hops.ops.stats["inner_iterations"], x.numpy().copy())
+        if sm == "chebyshev":
+            L0 = solver.mg.levels[0]
+            assert 1.5 < L0.rho < 3.5 and len(L0.omegas) == 2 and L0.omegas[0] < 2.0 / 3.0 < L0.omegas[1]
+            # the polynomial is a contraction on [rho/4, rho]
+            t = np.linspace(L0.rho / 4, L0.rho, 50)
+            assert np.abs((1 - L0.omegas[0] * t) * (1 - L0.omegas[1] * t)).max() < 0.25
+    assert out["chebyshev"][0] < out["jacobi"][0], (out["chebyshev"][0], out["jacobi"][0])
+    assert np.linalg.norm(out["chebyshev"][1] - out["jacobi"][1]) / np.linalg.norm(out["jacobi"][1]) < 1e-9
