@@ -152,9 +152,9 @@ class AMG:
         if len(self.omegas) != nu:
             raise ValueError("omega: one damping factor, or one per sweep")
         # smoother="chebyshev": the nu sweeps of a level use the roots of the degree-nu Chebyshev
-        # polynomial on [rho_l/4, rho_l], rho_l = 1.1 x a 20-step power-iteration estimate of rho(D^-1 P_l) made at
+        # polynomial on [rho_l/8, rho_l], rho_l = 1.1 x a 20-step power-iteration estimate of rho(D^-1 P_l) made at
         # every shift -- same kernels and cost as damped Jacobi, different damping per sweep and level.
-        # CPU double, annulus fixture: 47 -> 41 GMRES iterations per solve.  Off by default until timed
+        # CPU double, annulus fixture: 47 -> 38 GMRES iterations per solve (interval ratio 4: 41, 12: 38).  Off by default until timed
         # on the GPU (HX_AMG_SMOOTHER=chebyshev).
         self.smoother = smoother or os.environ.get("HX_AMG_SMOOTHER", "jacobi")
         if self.smoother not in ("jacobi", "chebyshev"):
@@ -401,7 +401,7 @@ class AMG:
         """The fine-level complex128 operator in its fastest SpMV format (SELL-32 when large)."""
         return self.levels[0].M64
 
-    def _chebyshev_dampings(self, L, iters=20, safety=1.1, alpha=4.0):
+    def _chebyshev_dampings(self, L, iters=20, safety=1.1, alpha=8.0):
         """1 / (roots of the degree-nu Chebyshev polynomial on [rho/alpha, rho]) for rho(D^-1 M_l)."""
         be = self.be
         gen = torch.Generator(device="cpu").manual_seed(1234 + L.n)
