@@ -195,6 +195,7 @@ class AMG:
             agg = torch.empty(n, dtype=torch.int64, device=dev)
             agg[order] = torch.arange(n, device=dev) // agg_size
             nc = int(agg.max().item()) + 1
+            L.agg = agg                           # dof -> aggregate (ownership of the coarse dofs on several GPUs)
             cnt = torch.bincount(agg, minlength=nc).to(f64)
             tval = 1.0 / torch.sqrt(cnt[agg])
             if getattr(be, "supports_spgemm", False) and n >= self.native_min_rows:

@@ -396,12 +396,108 @@ def _csr_transpose(M: CsrMatrix):
                      M.values[order].contiguous())
 
 
+class HaloPlan:
+    """Exchange plan of one distributed level: `own` global ids (ascending) first, then the `ghost` ids
+    grouped by owner.  Same exchange step as Partition.exchange (one gather + one grouped send/recv)."""
+
+    def __init__(self, world, rank, own, ghost, owner):
+        dev = own.device
+        self.world, self.rank = world, rank
+        self.n_own, self.n_ghost = int(own.numel()), int(ghost.numel())
+        gown = owner[ghost]
+        order = torch.sort(gown * (int(owner.numel()) + 1) + ghost).indices
+        ghost = ghost[order]
+        self.l2g = torch.cat([own, ghost])
+        self.ghost_owner_counts = torch.bincount(owner[ghost], minlength=world).cpu().numpy()
+        # every rank learns every ghost list and picks the ids it owns, in the requester's order
+        counts = _all_gather_rows(torch.tensor([self.n_ghost], dtype=torch.int64, device=dev), world).cpu().numpy()
+        allg = _all_gather_rows(ghost, world)
+        off = np.concatenate([[0], np.cumsum(counts)])
+        send_idx, send_counts = [], np.zeros(world, np.int64)
+        for q in range(world):
+            if q == rank:
+                continue
+            gq = allg[off[q]:off[q + 1]]
+            mine = gq[owner[gq] == rank]
+            send_idx.append(torch.searchsorted(own, mine))
+            send_counts[q] = int(mine.numel())
+        self.send_counts = send_counts
+        self.send_idx = torch.cat(send_idx) if send_idx else torch.zeros(0, dtype=torch.int64, device=dev)
+        self._plans = {}
+
+    @property
+    def n_loc(self):
+        return self.n_own + self.n_ghost
+
+    def exchange(self, x_loc):
+        if self.world == 1 or (self.n_ghost == 0 and self.send_idx.numel() == 0):
+            return x_loc
+        key = (x_loc.data_ptr(), x_loc.numel())
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) > 16:
+                self._plans.clear()
+            sendbuf = torch.zeros(max(int(self.send_idx.numel()), 1), dtype=x_loc.dtype, device=x_loc.device)
+            sreal = torch.view_as_real(sendbuf)
+            ghost = torch.view_as_real(x_loc[self.n_own:])
+            ops, soff, roff = [], 0, 0
+            for q in range(self.world):
+                if q == self.rank:
+                    continue
+                ns, nr = int(self.send_counts[q]), int(self.ghost_owner_counts[q])
+                if ns:
+                    ops.append(dist.P2POp(dist.isend, sreal[soff:soff + ns], q))
+                if nr:
+                    ops.append(dist.P2POp(dist.irecv, ghost[roff:roff + nr], q))
+                soff += ns
+                roff += nr
+            plan = (sendbuf, ops, x_loc)
+            self._plans[key] = plan
+        sendbuf, ops, _ = plan
+        if self.send_idx.numel():
+            torch.index_select(x_loc, 0, self.send_idx, out=sendbuf)
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return x_loc
+
+
+def _local_rows(M: CsrMatrix, own, g2l, n_loc):
+    """Rows `own` of the global matrix M with the columns renumbered by g2l; also the positions of
+    their values in M.values (to refresh the values at every shift)."""
+    ip = M.indptr.long()
+    cnt = (ip[1:] - ip[:-1])[own]
+    ptr = torch.zeros(own.numel() + 1, dtype=torch.int64, device=own.device)
+    ptr[1:] = torch.cumsum(cnt, 0)
+    total = int(ptr[-1])
+    pos = torch.repeat_interleave(ip[own] - ptr[:-1], cnt, output_size=total) + torch.arange(total, device=own.device)
+    cols = g2l[M.indices[pos].long()]
+    assert int(cols.min()) >= 0 if total else True, "a column of an owned row is neither owned nor in the halo"
+    # keep the columns of each row sorted (the CSR kernels and the diagonal search expect it)
+    rows = torch.repeat_interleave(torch.arange(own.numel(), device=own.device), cnt, output_size=total)
+    order = torch.sort(rows * n_loc + cols).indices
+    local = CsrMatrix(int(own.numel()), n_loc, ptr.to(torch.int32).contiguous(), cols[order].to(torch.int32).contiguous(),
+                      M.values[pos[order]].contiguous() if M.values is not None else None)
+    return local, pos[order]
+
+
+class _DLevel:
+    pass
+
+
 class DistHierarchy:
-    def __init__(self, space: "DistSpace", base, **amg_options):
+    """Replicated set-up, row-distributed cycle.  Levels with at least `min_rows` rows per rank are
+    distributed (smoothing, residual, restriction and prolongation on the owned rows, one halo exchange
+    per operator application); the rest of the hierarchy runs replicated on the all-reduced residual."""
+
+    def __init__(self, space: "DistSpace", base, min_rows=None, **amg_options):
+        import os
         from .amg import AMG
         part, be = space.part, space.local_be
         self.part, self.be, self.space = part, be, space
-        world = part.world
+        world, rank = part.world, part.rank
+        if min_rows is None:
+            min_rows = int(os.environ.get("HX_DIST_MIN_ROWS", "20000"))
         ip, ix = space._pattern
         dev = ip.device
         n_own, ng = part.n_own, part.n_global
@@ -420,58 +516,118 @@ class DistHierarchy:
         coords = torch.zeros(ng, 3, dtype=space.dof_coords.dtype, device=dev)
         coords[_all_gather_rows(l2g[:n_own], world)] = _all_gather_rows(space.dof_coords, world)
         B = glob(base["B"]) if base.get("B") is not None else None
-        self.mg = AMG(be, glob(base["A"]), glob(base["C"]), B, coords, **amg_options)
-        self.mg.use_graph = False
-        mg = self.mg
-        self.single, self.wdtype, self.nu, self.omegas = mg.single, mg.wdtype, mg.nu, mg.omegas
+        self.mg = mg = AMG(be, glob(base["A"]), glob(base["C"]), B, coords, **amg_options)
+        mg.use_graph = False
         if mg.smoother != "jacobi":
-            raise NotImplementedError("the distributed cycle uses constant damping on the fine level")
-        if len(mg.levels) < 2:
+            raise NotImplementedError("the distributed cycle uses constant damping")
+        self.single, self.wdtype, self.nu, self.omegas = mg.single, mg.wdtype, mg.nu, mg.omegas
+        nlev = len(mg.levels)
+        if nlev < 2:
             raise ValueError("the distributed cycle needs at least two levels")
-        own = l2g[:n_own]
-        self.P_own = _csr_rows(mg.levels[0].P, own)                     # n_own x n_1 (global coarse columns)
-        self.R_own = _csr_transpose(self.P_own)                         # n_1 x n_own
+        # ---- ownership per level: a coarse dof belongs to the lowest rank owning one of its members
+        owners = [torch.as_tensor(part.owner.astype(np.int64), device=dev)]
+        n_dist = 1
+        for l in range(1, nlev - 1):
+            if mg.levels[l].n < min_rows * world:
+                break
+            prev, agg = owners[-1], mg.levels[l - 1].agg
+            own_l = torch.full((mg.levels[l].n,), world, dtype=torch.int64, device=dev)
+            own_l.scatter_reduce_(0, agg, prev, reduce="amin", include_self=True)
+            owners.append(own_l)
+            n_dist = l + 1
+        self.n_dist = n_dist
         wd = self.wdtype
-        self.b = be.zeros(n_own, dtype=wd)
-        self.r = be.zeros(n_own, dtype=wd)
-        self.xa = be.zeros(part.n_loc, dtype=wd)
-        self.xb = be.zeros(part.n_loc, dtype=wd)
-        self.dinv = be.zeros(n_own)
-        self.M = None
+        self.dl = []
+        for l in range(n_dist):
+            D = _DLevel()
+            L = mg.levels[l]
+            D.own = torch.nonzero(owners[l] == rank).reshape(-1)
+            last_dist = l == n_dist - 1
+            # halo of level l: columns of the owned rows of M_l, of R_{l-1}... and of P_{l-1} rows of the level above
+            need = [_csr_rows(L.pattern, D.own).indices.long()]
+            if l > 0:
+                need.append(_csr_rows(mg.levels[l - 1].P, self.dl[l - 1].own).indices.long())
+            self._need = need
+            D.need = need
+            self.dl.append(D)
+        # restriction rows of the next distributed level read level-l residuals: extend level l's halo
+        for l in range(n_dist - 1):
+            Rn = _csr_rows(mg.levels[l].R, self.dl[l + 1].own)
+            self.dl[l].need.append(Rn.indices.long())
+        for l, D in enumerate(self.dl):
+            L = mg.levels[l]
+            allc = torch.unique(torch.cat(D.need))
+            ghost = allc[owners[l][allc] != rank]
+            D.halo = HaloPlan(world, rank, D.own, ghost, owners[l])
+            g2l = torch.full((L.n,), -1, dtype=torch.int64, device=dev)
+            g2l[D.halo.l2g] = torch.arange(D.halo.n_loc, device=dev)
+            D.g2l = g2l
+            D.M_pat, D.M_pos = _local_rows(L.pattern, D.own, g2l, D.halo.n_loc)
+            n_o, n_l = D.halo.n_own, D.halo.n_loc
+            D.b = be.zeros(n_o, dtype=wd)
+            D.r = be.zeros(n_l, dtype=wd)
+            D.xa = be.zeros(n_l, dtype=wd)
+            D.xb = be.zeros(n_l, dtype=wd)
+            D.dinv = be.zeros(n_o)
+            del D.need
+        for l, D in enumerate(self.dl):
+            L = mg.levels[l]
+            if l + 1 < n_dist:
+                Dn = self.dl[l + 1]
+                D.P, _ = _local_rows(L.P, D.own, Dn.g2l, Dn.halo.n_loc)           # own_l x loc_{l+1}
+                D.R, _ = _local_rows(L.R, Dn.own, D.g2l, D.halo.n_loc)            # own_{l+1} x loc_l
+            else:
+                D.P = _csr_rows(L.P, D.own)                                       # own_l x n_{l+1} (replicated below)
+                D.R = _csr_transpose(D.P)                                         # partial sums, all-reduced
+        assert torch.equal(self.dl[0].own, l2g[:n_own]), "level-0 ownership differs from the partition"
 
-    def set_fine(self, values_own):
-        """values_own: P(sigma) on the owned rows (space.pattern(), complex128), after mg.set_shift."""
-        ip, ix = self.space._pattern
-        M = CsrMatrix(self.part.n_own, self.part.n_loc, ip, ix, values_own)
-        self.be.diag_inv(M, self.dinv)
-        self.dinv_w = self.dinv.to(self.wdtype) if self.single else self.dinv
-        self.M = M.with_values(values_own.to(self.wdtype)) if self.single else M
+    def set_fine(self, values_own=None):
+        """Refresh the owned rows of every distributed level from the replicated level operators
+        (call after mg.set_shift)."""
+        be = self.be
+        for l, D in enumerate(self.dl):
+            vals = self.mg.levels[l].M.values[D.M_pos].contiguous()
+            M = D.M_pat.with_values(vals)
+            be.diag_inv(M, D.dinv)
+            D.dinv_w = D.dinv.to(self.wdtype) if self.single else D.dinv
+            D.M = M.with_values(vals.to(self.wdtype)) if self.single else M
 
-    def _sweeps(self, count, first_zero):
-        be, part, M = self.be, self.part, self.M
+    def _sweeps(self, D, first_zero):
+        be = self.be
         k = 0
         if first_zero:
-            be.jacobi_sweep(M, self.dinv_w, self.b, None, self.xa, self.omegas[0])
+            be.jacobi_sweep(D.M, D.dinv_w, D.b, None, D.xa, self.omegas[0])
             k = 1
-        for s in range(k, count):
-            part.exchange(self.xa)
-            be.jacobi_sweep(M, self.dinv_w, self.b, self.xa, self.xb, self.omegas[s])
-            self.xa, self.xb = self.xb, self.xa
+        for s in range(k, self.nu):
+            D.halo.exchange(D.xa)
+            be.jacobi_sweep(D.M, D.dinv_w, D.b, D.xa, D.xb, self.omegas[s])
+            D.xa, D.xb = D.xb, D.xa
+
+    def _cycle(self, l):
+        """V-cycle from distributed level l for the right-hand side in dl[l].b; result in dl[l].xa[:n_own]."""
+        be, mg, D = self.be, self.mg, self.dl[l]
+        self._sweeps(D, first_zero=True)
+        D.halo.exchange(D.xa)
+        be.spmv(D.M, D.xa, D.r, alpha=-1.0, beta=1.0, y0=D.b)                     # r = b - M x (owned rows)
+        if l + 1 < self.n_dist:
+            Dn = self.dl[l + 1]
+            D.halo.exchange(D.r)
+            be.spmv(D.R, D.r, Dn.b)
+            self._cycle(l + 1)
+            Dn.halo.exchange(Dn.xa)
+            be.spmv(D.P, Dn.xa, D.xa, alpha=1.0, beta=1.0, y0=D.xa)
+        else:
+            b1 = mg.levels[l + 1].b_
+            be.spmv(D.R, D.r, b1)
+            if self.part.world > 1:
+                dist.all_reduce(torch.view_as_real(b1))
+            x1 = mg._cycle(l + 1, b1)
+            be.spmv(D.P, x1, D.xa, alpha=1.0, beta=1.0, y0=D.xa)
+        self._sweeps(D, first_zero=False)
 
     def apply(self, v, out):
-        """out = V-cycle(v) on the owned entries: fine level distributed, levels >= 1 replicated."""
-        be, part, mg = self.be, self.part, self.mg
-        n_own = part.n_own
-        self.b.copy_(v)
-        self._sweeps(self.nu, first_zero=True)
-        part.exchange(self.xa)
-        be.spmv(self.M, self.xa, self.r, alpha=-1.0, beta=1.0, y0=self.b)           # r = b - M x
-        b1 = mg.levels[1].b_
-        be.spmv(self.R_own, self.r, b1)
-        if part.world > 1:
-            dist.all_reduce(torch.view_as_real(b1))
-        x1 = mg._cycle(1, b1)
-        be.spmv(self.P_own, x1, self.xa, alpha=1.0, beta=1.0, y0=self.xa)           # owned part of x += P x1
-        self._sweeps(self.nu, first_zero=False)
-        out.copy_(self.xa[:n_own])
+        D = self.dl[0]
+        D.b.copy_(v)
+        self._cycle(0)
+        out.copy_(D.xa[:D.halo.n_own])
         return out

@@ -70,6 +70,7 @@ def _synthetic_worker(rank, world, port, q, hierarchy=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["HX_DIST_HIERARCHY"] = "1" if hierarchy else "0"
+    os.environ["HX_DIST_MIN_ROWS"] = "50"           # small mesh: still distribute two levels
     _single_thread()
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -92,6 +93,8 @@ def _synthetic_worker(rank, world, port, q, hierarchy=False):
         ops = OperatorSet(space, space.own_values(vals["A"]), space.own_values(vals["C"]), space.own_values(vals["B"]))
         A, B, C = Mat(ops, {"A": 1.0}), Mat(ops, {"B": 1.0}), Mat(ops, {"C": 1.0})
         target = 3225.12 + 481.0j
+        if hierarchy:
+            ops.amg_options = {"coarse_max": 100}      # 2240 -> 140 -> 9 rows: two levels get distributed
         E = eigensolvers.pep_solver(A, B, C, target, nev=2)
         Eo = ox.pep_solve(ops_o.A, ops_o.B, ops_o.C, target, 2)
         assert abs(E.getEigenpair(0) - Eo.eigenvalues[0]) / abs(Eo.eigenvalues[0]) < 1e-8
@@ -100,11 +103,13 @@ def _synthetic_worker(rank, world, port, q, hierarchy=False):
             # the same eigen-solve on one rank: the row-distributed cycle is the single-rank cycle up to
             # summation order, so the inner iteration counts must agree
             assert ops.hierarchy() is not None and ops.amg() is ops.hierarchy().mg
+            assert ops.hierarchy().n_dist == 2 and all(D.halo.n_ghost > 0 for D in ops.hierarchy().dl)
             from tests.host_helpers import HostSpace
             V1 = HostSpace(ops_o.space, HostBackend())
             ops1 = OperatorSet(V1, torch.from_numpy(ox._on_pattern(ops_o.space, ops_o.A).real.copy()),
                                torch.from_numpy(ox._on_pattern(ops_o.space, ops_o.C).real.copy()),
                                torch.from_numpy(ox._on_pattern(ops_o.space, ops_o.B)))
+            ops1.amg_options = {"coarse_max": 100}
             E1 = eigensolvers.pep_solver(Mat(ops1, {"A": 1.0}), Mat(ops1, {"B": 1.0}), Mat(ops1, {"C": 1.0}), target, nev=2)
             assert abs(E1.getEigenpair(0) - E.getEigenpair(0)) / abs(E.getEigenpair(0)) < 1e-9
             single = ops1.stats["inner_iterations"]
