@@ -122,10 +122,11 @@ def _synthetic_worker(rank, world, port, q, hierarchy=False):
         dist.destroy_process_group()
 
 
-def _worker(rank, world, port, ordering, q):
+def _worker(rank, world, port, ordering, q, hierarchy=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["RANK"] = str(rank)
+    os.environ["HX_DIST_HIERARCHY"] = "1" if hierarchy else "0"
     _single_thread()
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -206,14 +207,14 @@ def _worker(rank, world, port, ordering, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ordering", ["morton"])
-def test_two_rank_partitioned_solve_matches_goldens(ordering):
+@pytest.mark.parametrize("ordering,hierarchy", [("morton", False), ("morton", True)])
+def test_two_rank_partitioned_solve_matches_goldens(ordering, hierarchy):
     """'input' ordering is only meaningful for meshes whose node order is already local
     (the structured synthetic annulus); gmsh node order is not, so Morton is the default."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ordering, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ordering, q, hierarchy)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
