@@ -20,6 +20,27 @@ c128 = torch.complex128
 #: allows" maps to these defaults, far inside the 1e-8 parity band on omega.
 DEFAULT_TOL = 1e-10
 INNER_RTOL = 1e-11
+# HX_INNER_RELAX=1: relaxed inexact Krylov-Schur -- the inner solve of an Arnoldi step is stopped at
+# INNER_RTOL * INNER_RELAX_SAFETY / r (at most INNER_RTOL_MAX), r = current relative Ritz residual of the
+# wanted pairs: late Arnoldi vectors do not need the accuracy of the first ones.  CPU double: PRF Rijke3D
+# fixed-point iteration 1912 -> 1234 inner iterations, RijkeFFD 2657 -> 1736, golden logs reproduced to the
+# same printed digits.  Off by default until timed on the GPU.
+import os as _os
+INNER_RELAX = _os.environ.get("HX_INNER_RELAX", "0") == "1"
+INNER_RELAX_SAFETY = 1.0
+INNER_RTOL_MAX = 1e-3
+
+
+def _relaxation(solvers):
+    """wanted_residual callback of krylov.krylov_schur for the given ShiftedSolver(s)."""
+    if not INNER_RELAX:
+        return None
+
+    def cb(r):
+        rtol = INNER_RTOL if not r else min(INNER_RTOL_MAX, max(INNER_RTOL, INNER_RTOL * INNER_RELAX_SAFETY / r))
+        for s_ in solvers:
+            s_.rtol = rtol
+    return cb
 
 
 class _Handle:
@@ -113,7 +134,8 @@ class EPS(_Handle):
             solver.solve(tmp, out)
 
         res = krylov.krylov_schur(be, op, n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit,
-                                  n_global=ops.n_global, v0=self.v0)
+                                  n_global=ops.n_global, v0=self.v0, wanted_residual=_relaxation([solver]))
+        solver.rtol = INNER_RTOL
         self._eig = sigma + 1.0 / res.theta
         self._X, self._its, self._nconv = res.X, res.its, res.nconv
         self.stats = {"n_apply": res.n_apply, "residuals": res.residuals}
@@ -127,7 +149,8 @@ class EPS(_Handle):
                 solver_t.solve(tmp, out)
 
             rt = krylov.krylov_schur(be, op_t, n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit, seed=1,
-                                     n_global=ops.n_global)
+                                     n_global=ops.n_global, wanted_residual=_relaxation([solver_t]))
+            solver_t.rtol = INNER_RTOL
             lam_t = sigma + 1.0 / rt.theta
             Y = be.zeros(len(self._eig), n)
             for i, lam in enumerate(self._eig):
@@ -180,7 +203,8 @@ class PEP(_Handle):
             be.axpby(-sigma, p, 1.0, out[n:])             # out_bot = u + sigma * out_top
 
         res = krylov.krylov_schur(be, op, 2 * n, self.nev, ncv=self.ncv, tol=self.tol, maxit=self.maxit,
-                                  n_global=2 * ops.n_global, v0=self.v0)
+                                  n_global=2 * ops.n_global, v0=self.v0, wanted_residual=_relaxation([solver]))
+        solver.rtol = INNER_RTOL
         self._eig = sigma + 1.0 / res.theta
         self._Xfull = res.X
         self._X = res.X[:, :n]

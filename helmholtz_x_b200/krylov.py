@@ -233,15 +233,27 @@ def _triu_eigvecs(R):
     return Y
 
 
+def _wanted_residual(r, nev):
+    theta, res, nconv = r[4], r[5], r[6]
+    hi = min(nev, len(theta))
+    if nconv >= hi:
+        return None
+    return float(max(res[i] / max(abs(theta[i]), 1e-300) for i in range(nconv, hi)))
+
+
 class KrylovSchurResult:
     def __init__(self, theta, X, its, nconv, residuals, n_apply):
         self.theta, self.X, self.its, self.nconv, self.residuals, self.n_apply = theta, X, its, nconv, residuals, n_apply
 
 
-def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, seed=0, n_global=None):
+def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, seed=0, n_global=None,
+                 wanted_residual=None):
     """nev eigenpairs of largest |theta| of the operator apply_op(v, out) on C^n.
     SLEPc defaults: ncv = max(2 nev, nev+15) (eigensolvers.py:58 passes DECIDE),
-    restart keeping half of the non-converged part."""
+    restart keeping half of the non-converged part.
+    wanted_residual(r): called before every operator application with the largest relative Ritz
+    residual of the wanted, not yet converged pairs (None while unknown) -- an inexact operator may
+    loosen its own tolerance as 1/r (relaxed inexact Krylov, Bouras-Fraysse / Simoncini-Szyld)."""
     import scipy.linalg as sla
     if ncv is None:
         ncv = max(2 * nev, nev + 15)
@@ -262,6 +274,8 @@ def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, 
     its = 0
     n_apply = 0
     Vnew = None
+    r_wanted = None
+
     def ritz(mm):
         """Ordered Schur form of the current mm x mm projection and the Ritz residual estimates."""
         T, Z = sla.schur(H[:mm, :mm], output="complex")
@@ -280,6 +294,8 @@ def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, 
         mm = m
         early = None
         for j in range(k, m):
+            if wanted_residual is not None:
+                wanted_residual(r_wanted)
             apply_op(V[j], w)
             n_apply += 1
             h, hb = basis.orthogonalize(j)
@@ -292,11 +308,13 @@ def krylov_schur(be, apply_op, n, nev, ncv=None, tol=1e-10, maxit=100, v0=None, 
             # pairs converge long before the basis is full -- test the small projection as we go
             if j + 1 >= max(nev + 2, k + 2) and j + 1 < m:
                 early = ritz(j + 1)
+                r_wanted = _wanted_residual(early, nev)
                 if early[-1] >= nev:
                     mm = j + 1
                     break
                 early = None
         T, Z, bt, Y, theta, res, nconv = early if early is not None else ritz(mm)
+        r_wanted = _wanted_residual((T, Z, bt, Y, theta, res, nconv), nev)
         if nconv >= nev or its >= maxit or mm < m:
             break
         keep = min(max(nconv + (m - nconv) // 2, nev), m - 1)

@@ -364,3 +364,20 @@ def test_chebyshev_damping_option(rijke):
             assert np.abs((1 - L0.omegas[0] * t) * (1 - L0.omegas[1] * t)).max() < 0.45
     assert out["chebyshev"][0] < out["jacobi"][0], (out["chebyshev"][0], out["jacobi"][0])
     assert np.linalg.norm(out["chebyshev"][1] - out["jacobi"][1]) / np.linalg.norm(out["jacobi"][1]) < 1e-9
+
+
+def test_relaxed_inner_tolerance_reproduces_golden_with_fewer_iterations(monkeypatch):
+    """HX_INNER_RELAX: inner solves of late Arnoldi steps stop at INNER_RTOL / (Ritz residual); the PRF
+    golden log (8 decimals) is reproduced with about a third fewer inner iterations."""
+    case = cases.prf_rijke3d()
+    gold = [cases.cplx(p) for p in G["prf_rijke3d_direct_fpi"]["omegas"]]
+    its = {}
+    for relax in (False, True):
+        monkeypatch.setattr(eigensolvers, "INNER_RELAX", relax)
+        hops = HostOperators(case)
+        D = HostFlame(case, hops)
+        E = eigensolvers.fixed_point_iteration(hops, D, case.target, nev=2, i=0)
+        for a, b in zip(E.omega_history[1:], gold):
+            assert abs(a - b) < 2e-8
+        its[relax] = hops.ops.stats["inner_iterations"]
+    assert its[True] < 0.8 * its[False], its

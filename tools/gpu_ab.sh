@@ -2,6 +2,7 @@
 # A/B timings of the options that were added after the last GPU run of round 1 (all CPU-validated):
 #   single-pass Gram-Schmidt in the inner GMRES (default on; HX_GMRES_ORTH=cgs2 = previous behaviour)
 #   W-cycle (HX_AMG_WCYCLE=1, default off)
+#   relaxed inner tolerance in the Krylov-Schur steps (HX_INNER_RELAX=1, default off)
 #   Chebyshev-root damping of the Jacobi sweeps (HX_AMG_SMOOTHER=chebyshev, default off)
 # usage: bash tools/gpu_ab.sh [dofs]     (one GPU; ~1 min per line at 1 M DoF)
 cd "$(dirname "$0")/.."
@@ -26,3 +27,5 @@ run cgs1_w1 HX_GMRES_ORTH=cgs1 HX_AMG_WCYCLE=1
 run cgs1_w2 HX_GMRES_ORTH=cgs1 HX_AMG_WCYCLE=2
 run cgs1_cheb HX_GMRES_ORTH=cgs1 HX_AMG_SMOOTHER=chebyshev
 run cgs1_cheb_w1 HX_GMRES_ORTH=cgs1 HX_AMG_SMOOTHER=chebyshev HX_AMG_WCYCLE=1
+run cgs1_relax HX_GMRES_ORTH=cgs1 HX_INNER_RELAX=1
+run cgs1_cheb_relax HX_GMRES_ORTH=cgs1 HX_AMG_SMOOTHER=chebyshev HX_INNER_RELAX=1
