@@ -542,13 +542,10 @@ class DistHierarchy:
             D = _DLevel()
             L = mg.levels[l]
             D.own = torch.nonzero(owners[l] == rank).reshape(-1)
-            last_dist = l == n_dist - 1
-            # halo of level l: columns of the owned rows of M_l, of R_{l-1}... and of P_{l-1} rows of the level above
-            need = [_csr_rows(L.pattern, D.own).indices.long()]
+            # halo of level l: columns of the owned rows of M_l and of the prolongator rows of the level above
+            D.need = [_csr_rows(L.pattern, D.own).indices.long()]
             if l > 0:
-                need.append(_csr_rows(mg.levels[l - 1].P, self.dl[l - 1].own).indices.long())
-            self._need = need
-            D.need = need
+                D.need.append(_csr_rows(mg.levels[l - 1].P, self.dl[l - 1].own).indices.long())
             self.dl.append(D)
         # restriction rows of the next distributed level read level-l residuals: extend level l's halo
         for l in range(n_dist - 1):
