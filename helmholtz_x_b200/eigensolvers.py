@@ -28,7 +28,7 @@ INNER_RTOL = 1e-11
 import os as _os
 INNER_RELAX = _os.environ.get("HX_INNER_RELAX", "0") == "1"
 INNER_RELAX_SAFETY = 1.0
-INNER_RTOL_MAX = 1e-3
+INNER_RTOL_MAX = 1e-4
 
 
 def _relaxation(solvers):
