@@ -23,7 +23,7 @@ INNER_RTOL = 1e-11
 # HX_INNER_RELAX=1: relaxed inexact Krylov-Schur -- the inner solve of an Arnoldi step is stopped at
 # INNER_RTOL * INNER_RELAX_SAFETY / r (at most INNER_RTOL_MAX), r = current relative Ritz residual of the
 # wanted pairs: late Arnoldi vectors do not need the accuracy of the first ones.  CPU double: PRF Rijke3D
-# fixed-point iteration 1912 -> 1234 inner iterations, RijkeFFD 2657 -> 1736, golden logs reproduced to the
+# fixed-point iteration 1912 -> 1273 inner iterations, RijkeFFD 2657 -> 1893, golden logs reproduced to the
 # same printed digits.  Off by default until timed on the GPU.
 import os as _os
 INNER_RELAX = _os.environ.get("HX_INNER_RELAX", "0") == "1"
