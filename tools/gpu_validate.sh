@@ -1,10 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=150 -k bloch > gpurun_out/pytest_bloch.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_bloch.log
-tail -15 gpurun_out/pytest_bloch.log
-timeout 700 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 --maxfail=10 --durations=8 > gpurun_out/pytest_gpu.log 2>&1
+# HX_TEST_EXPERIMENTAL=1 also runs the tests of the switches that are off by default
+timeout 900 env HX_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 --maxfail=10 --durations=8 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 grep -E "passed|failed|FAILED|Error" gpurun_out/pytest_gpu.log | head -12
 timeout 500 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
@@ -12,5 +10,5 @@ echo "exit $?" >> gpurun_out/bench_default.err
 python - <<PY
 import json
 b=json.loads(open('gpurun_out/bench_default.json').read().strip().split('\n')[-1])
-for k in ('value','e2e','gpu_launches','solver_stats','omega','roofline','cpu_baseline'): print(k, b.get(k))
+for k in ('value','e2e','gpu_launches','solver_stats','omega','roofline','iteration','cpu_baseline'): print(k, b.get(k))
 PY
