@@ -518,9 +518,7 @@ class DistHierarchy:
         B = glob(base["B"]) if base.get("B") is not None else None
         self.mg = mg = AMG(be, glob(base["A"]), glob(base["C"]), B, coords, **amg_options)
         mg.use_graph = False
-        if mg.smoother != "jacobi":
-            raise NotImplementedError("the distributed cycle uses constant damping")
-        self.single, self.wdtype, self.nu, self.omegas = mg.single, mg.wdtype, mg.nu, mg.omegas
+        self.single, self.wdtype, self.nu = mg.single, mg.wdtype, mg.nu
         nlev = len(mg.levels)
         if nlev < 2:
             raise ValueError("the distributed cycle needs at least two levels")
@@ -566,6 +564,9 @@ class DistHierarchy:
             D.xa = be.zeros(n_l, dtype=wd)
             D.xb = be.zeros(n_l, dtype=wd)
             D.dinv = be.zeros(n_o)
+            if mg.w_from is not None:
+                D.xs = be.zeros(n_l, dtype=wd)
+                D.bs = be.zeros(n_o, dtype=wd)
             del D.need
         for l, D in enumerate(self.dl):
             L = mg.levels[l]
@@ -588,16 +589,17 @@ class DistHierarchy:
             be.diag_inv(M, D.dinv)
             D.dinv_w = D.dinv.to(self.wdtype) if self.single else D.dinv
             D.M = M.with_values(vals.to(self.wdtype)) if self.single else M
+            D.omegas = self.mg.levels[l].omegas       # constant, or the level's Chebyshev roots of this shift
 
     def _sweeps(self, D, first_zero):
         be = self.be
         k = 0
         if first_zero:
-            be.jacobi_sweep(D.M, D.dinv_w, D.b, None, D.xa, self.omegas[0])
+            be.jacobi_sweep(D.M, D.dinv_w, D.b, None, D.xa, D.omegas[0])
             k = 1
         for s in range(k, self.nu):
             D.halo.exchange(D.xa)
-            be.jacobi_sweep(D.M, D.dinv_w, D.b, D.xa, D.xb, self.omegas[s])
+            be.jacobi_sweep(D.M, D.dinv_w, D.b, D.xa, D.xb, D.omegas[s])
             D.xa, D.xb = D.xb, D.xa
 
     def _cycle(self, l):
@@ -611,6 +613,14 @@ class DistHierarchy:
             D.halo.exchange(D.r)
             be.spmv(D.R, D.r, Dn.b)
             self._cycle(l + 1)
+            if mg.w_from is not None and mg.w_from <= l + 1:
+                # W-cycle: second visit of the (distributed) coarse level on its residual
+                Dn.xs.copy_(Dn.xa)
+                Dn.bs.copy_(Dn.b)
+                Dn.halo.exchange(Dn.xa)
+                be.spmv(Dn.M, Dn.xa, Dn.b, alpha=-1.0, beta=1.0, y0=Dn.bs)
+                self._cycle(l + 1)
+                Dn.xa[:Dn.halo.n_own] += Dn.xs[:Dn.halo.n_own]
             Dn.halo.exchange(Dn.xa)
             be.spmv(D.P, Dn.xa, D.xa, alpha=1.0, beta=1.0, y0=D.xa)
         else:
@@ -619,6 +629,13 @@ class DistHierarchy:
             if self.part.world > 1:
                 dist.all_reduce(torch.view_as_real(b1))
             x1 = mg._cycle(l + 1, b1)
+            if mg.w_from is not None and mg.w_from <= l + 1 < len(mg.levels) - 1:
+                Lc = mg.levels[l + 1]
+                Lc.xs.copy_(x1)
+                Lc.bs.copy_(b1)
+                be.spmv(Lc.Mop, Lc.xs, b1, alpha=-1.0, beta=1.0, y0=Lc.bs)
+                x1 = mg._cycle(l + 1, b1)
+                x1.add_(Lc.xs)
             be.spmv(D.P, x1, D.xa, alpha=1.0, beta=1.0, y0=D.xa)
         self._sweeps(D, first_zero=False)
 

@@ -318,10 +318,11 @@ def test_flexible_gmres_with_complex64_cycle_on_the_cpu_double(monkeypatch):
     assert hops.ops.stats["inner_iterations"] < 45
 
 
-def test_w_cycle_option_reduces_iterations_and_keeps_the_solution():
+def test_w_cycle_option_reduces_iterations_and_keeps_the_solution(monkeypatch):
     """AMG(w_from=1): levels >= 1 visited twice.  Same solution, fewer GMRES iterations (the option is
     off by default until it is timed on the GPU)."""
     from helmholtz_x_b200.operators import ShiftedSolver
+    monkeypatch.delenv("HX_AMG_WCYCLE", raising=False)
     case = cases.annulus()
     rng = np.random.default_rng(21)
     its, sols = {}, {}
