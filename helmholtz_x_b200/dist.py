@@ -145,6 +145,12 @@ class Partition:
                 req.wait()
         return x_loc
 
+    def all_reduce_max(self, t):
+        """In-place maximum over ranks of a real device scalar / tensor."""
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
     # ---- global <-> distributed host helpers -------------------------------------------
     def restrict_nodal(self, arr):
         return np.asarray(arr)[self.l2g]

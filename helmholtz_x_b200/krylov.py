@@ -68,50 +68,81 @@ class ArnoldiBasis:
 
 
 def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, basis=None, work=None, zbasis=None,
-          orth_passes=2):
-    """Right-preconditioned restarted GMRES: solves A x = b, x overwritten (start 0).
-    apply_A(v, out), precond(v, out).  Returns (iterations, relative residual).
+          orth_passes=2, anorm=None, eta=1e-14, x0=False, info=None):
+    """Right-preconditioned restarted GMRES: solves A x = b, x overwritten (start 0; x0=True: start
+    from the x passed in).  apply_A(v, out), precond(v, out).  Returns (iterations, relative residual).
     zbasis (restart x n): flexible GMRES -- the preconditioned vectors z_j = M^-1 v_j are kept
     and x += Z y, so the Arnoldi relation A Z = V H holds exactly even when the preconditioner
-    is not an exact linear operator (the complex64 multigrid cycle)."""
+    is not an exact linear operator (the complex64 multigrid cycle).
+
+    Every solve ends on a recomputed true residual r = b - A x.  It is accepted when
+    ||r|| <= rtol ||b||, or -- anorm given (an estimate of ||A||) -- when the normwise backward error
+    ||r|| / (anorm ||x||) <= eta: next to an eigenvalue of A (shift-invert at a converged shift, the
+    Newton iteration's singular L(omega_k)) ||x|| ~ ||b|| / |lambda_min| and rtol ||b|| lies below
+    what double precision can represent in A x; a backward-stable x is all an exact LU delivers
+    there, too.  info (dict): receives status ("converged" | "backward_stable" | "stagnated" |
+    "maxiter"), rel, eta (the backward error reached, None without anorm)."""
     n = b.numel()
     if basis is None:
         basis = ArnoldiBasis(be, n, restart)
     m = basis.m
     V, w = basis.V, basis.w
     z = work if work is not None else be.zeros(n)
-    x.zero_()
     nb = be.zeros(2)
-    be.multi_dot(b.view(1, -1), 1, b, nb)
-    bnorm = float(np.sqrt(nb[:1].cpu().numpy()[0].real))
+    info = info if info is not None else {}
+
+    def norm(v):
+        be.multi_dot(v.view(1, -1), 1, v, nb)
+        return float(np.sqrt(max(nb[:1].cpu().numpy()[0].real, 0.0)))
+
+    bnorm = norm(b)
+    if not x0:
+        x.zero_()
     if bnorm == 0.0:
+        x.zero_()
+        info.update(status="converged", rel=0.0, eta=0.0)
         return 0, 0.0
-    beta = bnorm
     total = 0
     rel = 1.0
-    first = True
-    estimate_converged = False
+    x_is_zero = not x0
+    claimed = False                 # the recurrence of the previous cycle reported convergence
     last_true = np.inf
-    while total < maxiter:
-        if not first:
-            # true residual r = b - A x
+    status = "maxiter"
+    eta_now = None
+    while True:
+        # true residual r = b - A x (the recurrence estimate is never the last word: single-pass
+        # Gram-Schmidt, complex64 preconditioner)
+        if x_is_zero:
+            beta = bnorm
+        else:
             apply_A(x, w)
             be.axpby(1.0, b, -1.0, w)             # w = b - w
-            be.multi_dot(w.view(1, -1), 1, w, nb)
-            beta = float(np.sqrt(max(nb[:1].cpu().numpy()[0].real, 0.0)))
-            rel = beta / bnorm
-            if rel <= rtol:
+            beta = norm(w)
+        rel = beta / bnorm
+        if rel <= rtol:
+            status = "converged"
+            break
+        if anorm is not None and not x_is_zero:
+            xnorm = norm(x)
+            eta_now = beta / (anorm * xnorm) if xnorm > 0.0 else None
+            if eta_now is not None and eta_now <= eta:
+                status = "backward_stable"
                 break
-            if estimate_converged:
-                # the recurrence says converged, the recomputed residual does not: refine with further
-                # cycles while they still help (near-singular shifts floor above rtol)
-                if rel > 0.5 * last_true:
-                    break
-                last_true = rel
-            be.scale_copy(w, V[0], alpha=1.0 / beta)
-        else:
+        if total >= maxiter:
+            status = "maxiter"
+            break
+        if claimed:
+            # the recurrence said converged, the recomputed residual does not: refine with further
+            # cycles while they still help
+            if rel > 0.5 * last_true:
+                status = "stagnated"
+                break
+            last_true = rel
+        claimed = False
+        if x_is_zero:
             be.scale_copy(b, V[0], alpha=1.0 / beta)
-            first = False
+        else:
+            be.scale_copy(w, V[0], alpha=1.0 / beta)
         # Givens QR of the Hessenberg matrix, column by column, in plain Python complex arithmetic
         # (NumPy scalar operations cost ~1 us each and this loop runs once per iteration)
         H = np.zeros((m + 1, m), complex)
@@ -120,6 +151,7 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
         cs = [0j] * m
         sn = [0j] * m
         j_used = 0
+
         def operator(jj):
             """w = A M^-1 v_jj (queued)."""
             if precond is not None and zbasis is not None:
@@ -164,9 +196,9 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
             g[j] = cs[j] * g[j]
             H[:j + 2, j] = col
             j_used = j + 1
-            rel = abs(g[j + 1]) / bnorm
-            if rel <= 0.9 * rtol or hb <= 1e-300:
-                estimate_converged = True
+            est = abs(g[j + 1]) / bnorm
+            if est <= 0.9 * rtol or hb <= 1e-300:
+                claimed = True
                 break
             if total >= maxiter:
                 break
@@ -184,10 +216,8 @@ def gmres(be, apply_A, b, x, precond=None, rtol=1e-10, restart=60, maxiter=600, 
                 be.axpby(1.0, z, 1.0, x)
             else:
                 be.axpby(1.0, w, 1.0, x)
-        if total >= maxiter:
-            break
-        # the loop head recomputes the true residual b - A x and stops there: the recurrence estimate
-        # is not trusted (single-pass Gram-Schmidt, complex64 preconditioner)
+        x_is_zero = False
+    info.update(status=status, rel=rel, eta=eta_now)
     return total, rel
 
 

@@ -47,6 +47,7 @@ class HostOperators:
         self.B = Mat(self.ops, {"B": 1.0}) if b is not None else None
         self.B_adj = Mat(self.ops, {"Bh": 1.0}) if b is not None else None
         self.C_nobc_values = c
+        self.V._mass = self.V.matrix(c.to(torch.complex128))      # eigenvectors._mass_form (no Dirichlet rows in these cases)
 
 
 class HostFlame:

@@ -503,23 +503,6 @@ def test_normalize_adjoint_config5_self_check():
     assert relmax(np.abs(p_adj_n.x.array), np.abs(pan)) < 1e-6
 
 
-def test_manufactured_config2_impedance_sweep():
-    """BASELINE config 2 (manufacturedHelmholtz.py): passive PEP with a Robin wall for several
-    impedances; GPU vs oracle to 1e-8 and vs the reference's analytic goldens (1 decimal, Hz)."""
-    from helmholtz_x_b200.eigensolvers import pep_solver
-    case = cases.manufactured()
-    for Z, f_gold in cases.manufactured_goldens()[::2]:
-        case["bcs"] = cases.manufactured_bcs(Z)
-        mats = gpu_operators(case)
-        target = 2 * np.pi * f_gold.real
-        E = pep_solver(mats.A, mats.B, mats.C, target, nev=2)
-        f = E.getEigenpair(0) / (2 * np.pi)
-        assert abs(f - f_gold) < 0.06 + 3e-5 * abs(f_gold), (Z, f, f_gold)
-        ops = cases.oracle_operators(case)
-        Eo = ox.pep_solve(ops.A, ops.B, ops.C, target, 2)
-        assert abs(E.getEigenpair(0) - Eo.eigenvalues[0]) / abs(Eo.eigenvalues[0]) < EIG_RTOL
-
-
 @pytest.mark.parametrize("degree", [1, 2])
 def test_shape_derivative_boundary_integral_matches_oracle(degree):
     """(f-1) helmholtz_x/shape_derivatives.py:12-37: int (V.n) div(conj(p_adj) c^2 grad p) ds on the

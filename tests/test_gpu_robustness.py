@@ -1,0 +1,90 @@
+"""GPU robustness corners of the inner solve (run after tests/test_gpu_parity.py: pytest orders files
+alphabetically and the driver stops at the first failure, so a corner cannot hide the core configs).
+
+The reference factorises the shifted operator exactly (PETSc LU / MUMPS behind
+helmholtz_x/eigensolvers.py:49-50,102-103), so a shift ON an eigenvalue, and Newton's sigma = 0 on the
+singular L(omega_k) (eigensolvers.py:278-348), simply work there.  Here the preconditioned GMRES has to
+stop on the normwise backward error (krylov.gmres) instead of ||r|| / ||b||."""
+import numpy as np
+import pytest
+
+from oracle import hx_oracle as ox
+from tests import cases
+from tests.gpu_helpers import gpu_flame, gpu_operators
+
+pytestmark = pytest.mark.gpu
+
+G = cases.golden_values()
+EIG_RTOL = 1e-8      # eigenvalue parity (north star)
+
+
+def test_manufactured_config2_impedance_sweep():
+    """BASELINE config 2 (manufacturedHelmholtz.py): passive PEP with a Robin wall for several
+    impedances; GPU vs oracle to 1e-8 and vs the reference's analytic goldens (1 decimal, Hz)."""
+    from helmholtz_x_b200.eigensolvers import pep_solver
+    case = cases.manufactured()
+    for Z, f_gold in cases.manufactured_goldens()[::2]:
+        case["bcs"] = cases.manufactured_bcs(Z)
+        mats = gpu_operators(case)
+        target = 2 * np.pi * f_gold.real
+        E = pep_solver(mats.A, mats.B, mats.C, target, nev=2)
+        f = E.getEigenpair(0) / (2 * np.pi)
+        assert abs(f - f_gold) < 0.06 + 3e-5 * abs(f_gold), (Z, f, f_gold)
+        ops = cases.oracle_operators(case)
+        Eo = ox.pep_solve(ops.A, ops.B, ops.C, target, 2)
+        assert abs(E.getEigenpair(0) - Eo.eigenvalues[0]) / abs(Eo.eigenvalues[0]) < EIG_RTOL
+
+
+
+def test_shift_next_to_an_eigenvalue():
+    """sigma at relative distance 1e-6, 1e-9 and 0 from the passive Rijke-tube eigenvalue
+    (RijkeTube3D/Results/Passive/passive.log:30-33)."""
+    from helmholtz_x_b200.eigensolvers import eps_solver
+    case = cases.rijke3d()
+    mats = gpu_operators(case, passive=True)
+    gold = np.sqrt(G["rijke3d_passive_eps"]["lambdas"][0])
+    E0 = eps_solver(mats.A, mats.C, case.target, nev=2)
+    om0 = min((np.sqrt(E0.getEigenvalue(i)) for i in range(2)), key=lambda z: abs(z - gold))
+    assert abs(om0 - gold) < 1e-9 * gold
+    stats = mats.A.ops.stats
+    for delta in (1e-6, 1e-9, 0.0):
+        s0, i0 = stats["inner_solves"], stats["inner_iterations"]
+        E = eps_solver(mats.A, mats.C, om0.real * (1 + delta), nev=2)
+        om = min((np.sqrt(E.getEigenvalue(i)) for i in range(2)), key=lambda z: abs(z - gold))
+        assert abs(om - gold) < 1e-9 * gold, (delta, om, gold)
+        assert stats["inner_iterations"] - i0 < 120 * (stats["inner_solves"] - s0), (delta, stats)
+    assert stats.get("floor_accepts", 0) > 0
+
+
+def test_shift_on_an_eigenvalue_of_the_annulus_pep():
+    """Same corner on config 3's passive operators (Robin outlet => PEP, 34,787 dofs): a computed
+    eigenvalue is used as the target of one more eigen-solve."""
+    from helmholtz_x_b200.eigensolvers import pep_solver
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    E = pep_solver(mats.A, mats.B, mats.C, case.target, nev=2)
+    om = E.getEigenpair(0)
+    for delta in (1e-7, 0.0):
+        E2 = pep_solver(mats.A, mats.B, mats.C, om * (1 + delta), nev=2)
+        om2 = min((E2.getEigenpair(i) for i in range(2)), key=lambda z: abs(z - om))
+        assert abs(om2 - om) < 1e-9 * abs(om), (delta, om2, om)
+
+
+def test_newton_to_tol_1e_6_annulus():
+    """newtonSolver (eigensolvers.py:278-348) far past the golden run's tol 1e-2: two-sided EPS at
+    sigma = 0 on an operator whose smallest eigenvalue goes to zero with the Newton residual."""
+    from helmholtz_x_b200.eigensolvers import newtonSolver
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    D = gpu_flame(case, mats.mesh)
+    D.assemble_submatrices()
+    omega, p = newtonSolver(mats, D, case.newton_init, i=0, nev=case.newton_nev, tol=1e-6)
+    # the Newton limit is a root of the nonlinear eigenproblem: L(omega) has a zero eigenvalue
+    D.assemble_matrix(omega)
+    L = mats.A + omega * mats.B + omega ** 2 * mats.C - D.matrix
+    from helmholtz_x_b200.eigensolvers import eps_solver
+    E = eps_solver(L, -mats.C, 0, 2)
+    lam = min(abs(E.getEigenvalue(i)) for i in range(2))
+    assert lam < 1e-4 * abs(omega), (omega, lam)       # |d lambda / d omega| ~ 2 |omega|: |delta omega| < 1e-4
+    g = cases.cplx(G["annulus_newton_eigenvalues"]["direct_1"])
+    assert abs(omega - g) < 2e-2 * 10                   # same root as the golden run (which stopped at 1e-2)

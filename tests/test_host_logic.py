@@ -382,3 +382,59 @@ def test_relaxed_inner_tolerance_reproduces_golden_with_fewer_iterations(monkeyp
             assert abs(a - b) < 2e-8
         its[relax] = hops.ops.stats["inner_iterations"]
     assert its[True] < 0.8 * its[False], its
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_shift_next_to_an_eigenvalue_is_solved_to_backward_stability(monkeypatch, mixed):
+    """shift-invert with sigma at relative distance 1e-6 / 1e-9 / 0 from an eigenvalue
+    (helmholtz_x/eigensolvers.py:41-67 with an exact LU simply works there).  ||b - P x|| / ||b|| cannot
+    reach 1e-11 next to a singular P; the inner solve stops on the normwise backward error instead and the
+    eigenvalue still comes out to 1e-9."""
+    monkeypatch.setattr(HostBackend, "supports_mixed", mixed)
+    case = cases.rijke3d()
+    hops = HostOperators(case, passive=True)
+    gold = np.sqrt(G["rijke3d_passive_eps"]["lambdas"][0])
+    E0 = eigensolvers.eps_solver(hops.A, hops.C, case.target, nev=2)
+    om0 = min((np.sqrt(E0.getEigenvalue(i)) for i in range(2)), key=lambda z: abs(z - gold))
+    assert abs(om0 - gold) < 1e-9 * gold
+    for delta in (1e-6, 1e-9, 0.0):
+        hops.ops._shift_state = None
+        s0, i0 = hops.ops.stats["inner_solves"], hops.ops.stats["inner_iterations"]
+        E = eigensolvers.eps_solver(hops.A, hops.C, om0.real * (1 + delta), nev=2)
+        om = min((np.sqrt(E.getEigenvalue(i)) for i in range(2)), key=lambda z: abs(z - gold))
+        assert abs(om - gold) < 1e-9 * gold, (delta, om, gold)
+        n_solves = hops.ops.stats["inner_solves"] - s0
+        assert hops.ops.stats["inner_iterations"] - i0 < 120 * n_solves, (delta, hops.ops.stats)
+    assert hops.ops.stats.get("floor_accepts", 0) > 0            # the backward-error exit was actually taken
+
+
+def test_gmres_reports_the_true_residual_on_every_exit(rijke):
+    """ADVICE r1 (krylov.py:187): maxiter exits return a recomputed residual, never the recurrence estimate."""
+    _, hops = rijke
+    be = hops.ops.be
+    P = hops.ops.space.matrix(hops.ops.combine({"A": 1.0, "C": (400 * np.pi) ** 2}))
+    Ps = P.to_scipy()
+    b = torch.randn(P.n_rows, dtype=torch.float64, generator=torch.Generator().manual_seed(3)).to(torch.complex128)
+    x = torch.zeros_like(b)
+    info = {}
+    its, rel = krylov.gmres(be, lambda v, o: be.spmv(P, v, o), b, x, rtol=1e-12, restart=10, maxiter=25, info=info)
+    assert its == 25 and info["status"] == "maxiter"
+    true = np.linalg.norm(Ps @ x.numpy() - b.numpy()) / np.linalg.norm(b.numpy())
+    assert abs(rel - true) <= 1e-12 * max(true, 1.0) + 1e-14
+    # continuing from that x (x0=True) picks up where it stopped
+    its2, rel2 = krylov.gmres(be, lambda v, o: be.spmv(P, v, o), b, x, rtol=1e-12, restart=10, maxiter=25, x0=True)
+    assert rel2 < rel
+
+
+def test_newton_to_a_tight_tolerance_on_the_singular_operator(monkeypatch):
+    """helmholtz_x/eigensolvers.py:278-348: every Newton step shift-inverts L(omega_k) at sigma = 0, and
+    L(omega_k) becomes singular as omega_k converges.  tol 1e-6 (the golden runs stop at 1e-2)."""
+    monkeypatch.setattr(HostBackend, "supports_mixed", True)
+    case = cases.rijke3d()
+    hops = HostOperators(case)
+    D = HostFlame(case, hops)
+    gold = cases.cplx(G["rijke3d_active_fpi"]["omegas"][-1])
+    omega, p = eigensolvers.newtonSolver(hops, D, gold * (1 + 2e-3), nev=2, i=0, tol=1e-6)
+    om_o, _, _ = ox.newton_solver(hops.oracle, cases.oracle_flame(case), gold * (1 + 2e-3), nev=2, i=0, tol=1e-6)
+    assert abs(omega - om_o) < 1e-8 * abs(om_o), (omega, om_o)
+    assert abs(omega - gold) < 1e-5 * abs(gold)
