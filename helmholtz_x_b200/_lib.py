@@ -64,6 +64,7 @@ SIGNATURES = {
     "hx_dof_cell_count": [i64, i32, vp, i32, vp, vp],
     "hx_dof_cell_fill": [i64, i32, vp, i32, vp, vp, vp, vp],
     "hx_pattern_rows": [i32, i32, vp, vp, vp, vp, vp, vp, i32, vp],
+    "hx_color_cells": [i64, i32, vp, vp, vp, vp, vp, i32, vp, vp],
     "hx_color_cells_h": [i64, i32, vp, i32, vp],
     "hx_assemble_AC": [i32, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp],
     "hx_assemble_B": [i32, i64, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp],
@@ -76,6 +77,12 @@ SIGNATURES = {
     "hx_point_dphidz": [i32, vp, vp, i32, vp, vp, vp, vp],
     "hx_shape_derivative": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_threshold": [i64, vp, f64, vp],
+    "hx_peer_alloc": [i64, vp, vp],
+    "hx_peer_open": [vp, vp],
+    "hx_peer_close": [vp],
+    "hx_peer_free": [vp],
+    "hx_peer_halo_exchange": [vp, vp, i32, vp],
+    "hx_peer_allreduce": [vp, vp, vp, i64, i32, vp],
 }
 _RESTYPES = {"hx_last_error": C.c_char_p, "hx_launch_count": i64, "hx_reduce_scratch_bytes": i64,
              "hx_launch_count_reset": None, "hx_launch_count_add": None}

@@ -5,6 +5,7 @@ import numpy as np
 from . import fem
 from .operators import Mat, OperatorSet
 from .parameters_utils import gamma_function, sound_speed_variable_gamma
+from .phases import phase
 from .solver_utils import info, rank0
 
 
@@ -86,7 +87,8 @@ class AcousticMatrices:
             else:
                 c_asm = fem.Function(Vasm, part.restrict_nodal(cvals[:mesh.n_nodes]), dtype=np.float64)
             bc_dofs = [part.g2l[d][part.g2l[d] >= 0] for d in bc_dofs]
-        a_vals, c_vals = fem.assemble_AC(Vasm, c_asm)
+        with phase("assembly_fields"):
+            a_vals, c_vals = fem.assemble_AC(Vasm, c_asm)
         self.C_nobc_values = c_vals
         if bc_dofs:
             dofs = np.unique(np.concatenate(bc_dofs))
@@ -97,7 +99,8 @@ class AcousticMatrices:
         info("- Matrix A is assembled.")
         b_vals = None
         if terms:
-            b_vals = fem.assemble_B(Vasm, c_asm, terms)
+            with phase("assembly_B"):
+                b_vals = fem.assemble_B(Vasm, c_asm, terms)
             info("- Matrix B is assembled.")
         if part is not None:
             self.V = DistSpace(part, Vasm)

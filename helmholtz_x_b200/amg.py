@@ -132,6 +132,8 @@ class Level:
 #: i.e. over-relaxes the prolongator smoothing, which measured BEST (25 vs 30 GMRES iterations at 60k DoF,
 #: 36 vs 45 at 250k); "gershgorin" = max_i sum_j |k_ij| / k_ii (safe upper bound); "power" = random start
 RHO_MODE = "smoothpower"
+#: fine-level rows from which the W-cycle pays on B200 (see AMG.__init__)
+W_AUTO_MIN_ROWS = 3_000_000
 
 
 class AMG:
@@ -142,10 +144,12 @@ class AMG:
         precision="single": the V-cycle (smoother, residual, transfers) runs in complex64 --
         it is only a preconditioner; GMRES and everything outside stay complex128."""
         self.be, self.nu, self.omega = be, nu, omega
-        # W-cycle: levels >= w_from are visited twice per visit of their parent (None: V-cycle).  Measured
-        # on the CPU double (GMRES iterations per solve, synthetic annulus): 250 k DoF V 37, W from level 1
-        # 29, W from level 2 33; the V-cycle count grows with the number of levels, the W-cycle count
-        # hardly does.  Off by default until timed on the GPU (HX_AMG_WCYCLE=<level>).
+        # W-cycle: levels >= w_from are visited twice per visit of their parent (None: V-cycle).  The
+        # V-cycle count grows with the number of levels, the W-cycle count hardly does; the extra coarse
+        # visits are latency-bound.  Measured on B200 (profiles/r2_ab_switches.md, synthetic annulus, whole
+        # step): 1 M DoF V 3.53 s / W from level 1 4.01 s; 10 M DoF V 50.5 s / W 43.8 s (inner iterations
+        # 7108 -> 4388).  Default (HX_AMG_WCYCLE unset or "auto"): W from level 1 on meshes of at least
+        # W_AUTO_MIN_ROWS rows, V below; HX_AMG_WCYCLE=<level> forces it, "off" forces the V-cycle.
         # damping of sweep s (pre- and post-smoothing alike); a list makes the nu sweeps a polynomial
         # smoother with those roots (e.g. the Chebyshev pair) at no extra cost
         self.omegas = list(omega) if isinstance(omega, (list, tuple)) else [omega] * nu
@@ -154,13 +158,19 @@ class AMG:
         # smoother="chebyshev": the nu sweeps of a level use the roots of the degree-nu Chebyshev
         # polynomial on [rho_l/8, rho_l], rho_l = 1.1 x a 20-step power-iteration estimate of rho(D^-1 P_l) made at
         # every shift -- same kernels and cost as damped Jacobi, different damping per sweep and level.
-        # CPU double, annulus fixture: 47 -> 38 GMRES iterations per solve (interval ratio 4: 41, 12: 38).  Off by default until timed
-        # on the GPU (HX_AMG_SMOOTHER=chebyshev).
-        self.smoother = smoother or os.environ.get("HX_AMG_SMOOTHER", "jacobi")
+        # The default since it was timed on B200 (profiles/r2_ab_switches.md): whole step at 1 M DoF 5.35 ->
+        # 4.31 s (inner iterations 7410 -> 5666); HX_AMG_SMOOTHER=jacobi restores constant damping.
+        self.smoother = smoother or os.environ.get("HX_AMG_SMOOTHER", "chebyshev")
         if self.smoother not in ("jacobi", "chebyshev"):
             raise ValueError("smoother must be 'jacobi' or 'chebyshev'")
-        if w_from is None and os.environ.get("HX_AMG_WCYCLE"):
-            w_from = int(os.environ["HX_AMG_WCYCLE"])
+        if w_from is None:
+            env = os.environ.get("HX_AMG_WCYCLE", "auto")
+            if env == "auto":
+                w_from = 1 if A.n_rows >= W_AUTO_MIN_ROWS else None
+            elif env not in ("off", ""):
+                w_from = int(env)
+        elif w_from == "off":
+            w_from = None
         self.w_from = w_from
         self.native_min_rows = 20000
         # the V-cycle is a fixed sequence of ~25 small launches on fixed buffers: captured once per

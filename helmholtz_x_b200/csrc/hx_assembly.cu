@@ -598,6 +598,54 @@ __global__ void dof_cell_fill_kernel(long long total, int nd, const int* __restr
     adj_cells[adj_ptr[dof] + slot] = (int)(t / nd);
 }
 
+// ---- deterministic colouring on the device (Jones-Plassmann with fixed hashed priorities) ----------
+// Cells (or facets) conflict when they share a vertex.  Per round every uncoloured cell whose
+// priority beats all its uncoloured neighbours takes the smallest colour none of its neighbours
+// holds.  Decisions read only the state at the START of the round (ping-pong arrays), so the
+// colouring depends on the mesh alone -- not on scheduling -- and the colour-ordered scatter of
+// the assembly kernels stays bitwise reproducible.
+__device__ __forceinline__ unsigned int color_priority(unsigned int c) {
+    unsigned int h = c * 0x9E3779B1u;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+__global__ void __launch_bounds__(256)
+color_round_kernel(long long n_cells, int nv, const int* __restrict__ cells, const int* __restrict__ adj_ptr,
+                   const int* __restrict__ adj_cells, const int* __restrict__ cin, int* __restrict__ cout,
+                   unsigned long long* __restrict__ remaining) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    int mine = cin[c];
+    if (mine == -1) {
+        const unsigned int pc = color_priority((unsigned int)c);
+        unsigned long long forb0 = 0ull, forb1 = 0ull;
+        bool is_max = true;
+        for (int k = 0; k < nv && is_max; ++k) {
+            const int v = cells[c * nv + k];
+            const int s = adj_ptr[v], e = adj_ptr[v + 1];
+            for (int t = s; t < e; ++t) {
+                const int nb = adj_cells[t];
+                if (nb == (int)c) continue;
+                const int col = cin[nb];
+                if (col < 0) {
+                    const unsigned int pn = color_priority((unsigned int)nb);
+                    if (pn > pc || (pn == pc && nb > (int)c)) { is_max = false; break; }
+                } else if (col < 64) forb0 |= 1ull << col;
+                else forb1 |= 1ull << (col - 64);
+            }
+        }
+        if (is_max) {
+            if (~forb0) mine = __ffsll((long long)~forb0) - 1;
+            else if (~forb1) mine = 64 + __ffsll((long long)~forb1) - 1;
+            else mine = -2;                      // more than 128 colours: reported by the host wrapper
+        } else {
+            atomicAdd(remaining, 1ull);
+        }
+    }
+    cout[c] = mine;
+}
+
 // one warp per row: gather the dofs of all incident cells, rank-sort + unique.
 constexpr int kPatWarps = 4;
 constexpr int kPatCap = 2048;
@@ -674,6 +722,26 @@ extern "C" int hx_pattern_rows(int n_dofs, int nd, const int32_t* cell_dofs, con
     pattern_rows_kernel<<<ceil_div(n_dofs, kPatWarps), kPatWarps * 32, 0, (cudaStream_t)stream>>>(
         n_dofs, nd, cell_dofs, adj_ptr, adj_cells, row_nnz, indptr, indices, write_cols);
     return check_launch("pattern_rows_kernel");
+}
+
+extern "C" int hx_color_cells(int64_t n_cells, int nv, const int32_t* cells, const int32_t* adj_ptr,
+                              const int32_t* adj_cells, int32_t* color_a, int32_t* color_b, int rounds,
+                              uint64_t* remaining_dev, hx_stream_t stream) {
+    if (n_cells <= 0) return HX_OK;
+    if (rounds < 2 || (rounds & 1)) return fail(HX_ERR_ARG, "hx_color_cells: rounds must be even and >= 2%s%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)ceil_div<long long>(n_cells, 256);
+    int32_t* cin = color_a;
+    int32_t* cout = color_b;
+    for (int r = 0; r < rounds; ++r) {
+        HX_CUDA(cudaMemsetAsync(remaining_dev, 0, sizeof(uint64_t), st));
+        color_round_kernel<<<blocks, 256, 0, st>>>(n_cells, nv, cells, adj_ptr, adj_cells, cin, cout,
+                                                  (unsigned long long*)remaining_dev);
+        int rc = check_launch("color_round_kernel");
+        if (rc) return rc;
+        int32_t* t = cin; cin = cout; cout = t;
+    }
+    return HX_OK;            // result in color_a; *remaining_dev = cells still uncoloured
 }
 
 extern "C" int hx_color_cells_h(int64_t n_cells, int nv, const int32_t* cells_h, int n_nodes, int32_t* color_h) {

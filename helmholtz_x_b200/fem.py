@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from .backend import CsrMatrix, CudaBackend
+from .phases import phase
 
 f64 = torch.float64
 i32 = torch.int32
@@ -102,30 +103,65 @@ class Mesh:
             self._part = part
         return self._part
 
-    # -- colouring (host integer preprocessing through the C-ABI) --------------------------
+    # -- colouring (device: Jones-Plassmann rounds with fixed priorities, hx_color_cells) ------------
     @staticmethod
-    def _color(entities, n_nodes, be):
-        ent = np.ascontiguousarray(entities, dtype=np.int32)
-        color = np.empty(len(ent), np.int32)
-        nc = _lib.call("hx_color_cells_h", len(ent), ent.shape[1], ent.ctypes.data_as(C.c_void_p), n_nodes,
-                       color.ctypes.data_as(C.c_void_p))
-        if nc < 0:
-            raise _lib.HxError("hx_color_cells_h failed: " + _lib.load().hx_last_error().decode())
-        order = np.argsort(color, kind="stable").astype(np.int32)
+    def _color(entities_d, n_nodes, be):
+        """entities_d: (n, nv) int32 device tensor.  Returns (#colours, host int64 colour pointer,
+        device int32 entity order grouped by colour, ascending entity index inside a colour)."""
+        ent = entities_d.contiguous()
+        n, nv = int(ent.shape[0]), int(ent.shape[1])
+        if n == 0:
+            return 0, np.zeros(1, np.int64), be.zeros(0, dtype=i32), be.zeros(0, dtype=i32)
+        st = be.stream
+        count = be.zeros(n_nodes, dtype=i32)
+        _lib.call("hx_dof_cell_count", n, nv, ent.data_ptr(), n_nodes, count.data_ptr(), st)
+        adj_ptr = be.zeros(n_nodes + 1, dtype=i32)
+        adj_ptr[1:] = torch.cumsum(count, 0)
+        cursor = be.zeros(n_nodes, dtype=i32)
+        adj = be.empty(n * nv, dtype=i32)
+        _lib.call("hx_dof_cell_fill", n, nv, ent.data_ptr(), n_nodes, adj_ptr.data_ptr(), cursor.data_ptr(), adj.data_ptr(), st)
+        ca = torch.full((n,), -1, dtype=i32, device=be.device)
+        cb = torch.empty_like(ca)
+        remaining = torch.zeros(1, dtype=torch.int64, device=be.device)
+        for _ in range(512):
+            _lib.call("hx_color_cells", n, nv, ent.data_ptr(), adj_ptr.data_ptr(), adj.data_ptr(), ca.data_ptr(),
+                      cb.data_ptr(), 8, remaining.data_ptr(), st)
+            if int(remaining) == 0:
+                break
+        else:
+            raise _lib.HxError("hx_color_cells did not finish")
+        if int(ca.min()) < 0:
+            raise _lib.HxError("hx_color_cells: more than 128 colours needed")
+        nc = int(ca.max()) + 1
+        order = torch.sort(ca, stable=True).indices.to(i32)
         ptr = np.zeros(nc + 1, np.int64)
-        ptr[1:] = np.cumsum(np.bincount(color, minlength=nc))
-        return nc, ptr, be.asarray(order, dtype=i32)
+        ptr[1:] = torch.cumsum(torch.bincount(ca, minlength=nc), 0).cpu().numpy()
+        return nc, ptr, order.contiguous(), ca
 
     def cell_colors(self):
+        """(#colours, host colour pointer, device cell order grouped by colour)."""
         if self._cell_colors is None:
-            self._cell_colors = self._color(self.cells, self.n_nodes, self.be)
-        return self._cell_colors
+            with phase("colouring"):
+                self._cell_colors = self._color(self.cellsd, self.n_nodes, self.be)
+        return self._cell_colors[:3]
+
+    def tagged_cell_colors(self, tag):
+        """The same triple restricted to the cells carrying `tag` (flame zones are a small part of
+        the mesh: the flame-vector kernels then visit those cells only)."""
+        self.cell_colors()
+        nc, _, _, ca = self._cell_colors
+        sel = torch.nonzero(self.cell_tagsd == int(tag)).reshape(-1)
+        col = ca[sel]
+        order = torch.sort(col, stable=True).indices
+        ptr = np.zeros(nc + 1, np.int64)
+        ptr[1:] = torch.cumsum(torch.bincount(col, minlength=nc), 0).cpu().numpy()
+        return nc, ptr, sel[order].to(i32).contiguous()
 
     def facet_colors(self, tag):
         if tag not in self._facet_colors:
-            sel = np.flatnonzero(self.facet_tags == tag).astype(np.int32)
-            nc, ptr, order = self._color(self.facets[sel], self.n_nodes, self.be)
-            self._facet_colors[tag] = (nc, ptr, self.be.asarray(sel, dtype=i32)[order.long()].contiguous())
+            sel = self.be.asarray(np.flatnonzero(self.facet_tags == tag), dtype=torch.int64)
+            nc, ptr, order, _ = self._color(self.facetsd[sel], self.n_nodes, self.be)
+            self._facet_colors[tag] = (nc, ptr, sel[order.long()].to(i32).contiguous())
         return self._facet_colors[tag]
 
     def volumes(self):
@@ -196,33 +232,37 @@ class FunctionSpace:
     # -- K4: CSR pattern ---------------------------------------------------------------------
     def pattern(self):
         if self._pattern is None:
-            be, m = self.be, self.mesh
-            st = be.stream
-            n, nd, ncell = self.n, self.nd, m.n_cells
-            count = be.zeros(n, dtype=i32)
-            _lib.call("hx_dof_cell_count", ncell, nd, self.cell_dofs.data_ptr(), n, count.data_ptr(), st)
-            adj_ptr = be.zeros(n + 1, dtype=i32)
-            adj_ptr[1:] = torch.cumsum(count, 0)
-            cursor = be.zeros(n, dtype=i32)
-            adj = be.empty(ncell * nd, dtype=i32)
-            _lib.call("hx_dof_cell_fill", ncell, nd, self.cell_dofs.data_ptr(), n, adj_ptr.data_ptr(), cursor.data_ptr(),
-                      adj.data_ptr(), st)
-            row_nnz = be.zeros(n, dtype=i32)
-            _lib.call("hx_pattern_rows", n, nd, self.cell_dofs.data_ptr(), adj_ptr.data_ptr(), adj.data_ptr(),
-                      row_nnz.data_ptr(), None, None, 0, st)
-            if int(row_nnz.min()) < 0:
-                raise _lib.HxError("pattern build: a dof touches too many cells for the row buffer")
-            indptr = be.zeros(n + 1, dtype=torch.int64)
-            indptr[1:] = torch.cumsum(row_nnz.long(), 0)
-            nnz = int(indptr[-1])
-            if nnz >= 2 ** 31:
-                raise _lib.HxError("pattern build: nnz exceeds int32 indexing")
-            indptr = indptr.to(i32).contiguous()
-            indices = be.empty(nnz, dtype=i32)
-            _lib.call("hx_pattern_rows", n, nd, self.cell_dofs.data_ptr(), adj_ptr.data_ptr(), adj.data_ptr(),
-                      row_nnz.data_ptr(), indptr.data_ptr(), indices.data_ptr(), 1, st)
-            self._pattern = (indptr, indices)
+            with phase("pattern"):
+                self._build_pattern()
         return self._pattern
+
+    def _build_pattern(self):
+        be, m = self.be, self.mesh
+        st = be.stream
+        n, nd, ncell = self.n, self.nd, m.n_cells
+        count = be.zeros(n, dtype=i32)
+        _lib.call("hx_dof_cell_count", ncell, nd, self.cell_dofs.data_ptr(), n, count.data_ptr(), st)
+        adj_ptr = be.zeros(n + 1, dtype=i32)
+        adj_ptr[1:] = torch.cumsum(count, 0)
+        cursor = be.zeros(n, dtype=i32)
+        adj = be.empty(ncell * nd, dtype=i32)
+        _lib.call("hx_dof_cell_fill", ncell, nd, self.cell_dofs.data_ptr(), n, adj_ptr.data_ptr(), cursor.data_ptr(),
+                  adj.data_ptr(), st)
+        row_nnz = be.zeros(n, dtype=i32)
+        _lib.call("hx_pattern_rows", n, nd, self.cell_dofs.data_ptr(), adj_ptr.data_ptr(), adj.data_ptr(),
+                  row_nnz.data_ptr(), None, None, 0, st)
+        if int(row_nnz.min()) < 0:
+            raise _lib.HxError("pattern build: a dof touches too many cells for the row buffer")
+        indptr = be.zeros(n + 1, dtype=torch.int64)
+        indptr[1:] = torch.cumsum(row_nnz.long(), 0)
+        nnz = int(indptr[-1])
+        if nnz >= 2 ** 31:
+            raise _lib.HxError("pattern build: nnz exceeds int32 indexing")
+        indptr = indptr.to(i32).contiguous()
+        indices = be.empty(nnz, dtype=i32)
+        _lib.call("hx_pattern_rows", n, nd, self.cell_dofs.data_ptr(), adj_ptr.data_ptr(), adj.data_ptr(),
+                  row_nnz.data_ptr(), indptr.data_ptr(), indices.data_ptr(), 1, st)
+        self._pattern = (indptr, indices)
 
     def matrix(self, values):
         indptr, indices = self.pattern()
@@ -306,13 +346,33 @@ class Function:
     def __init__(self, V, values=None, dtype=np.complex128, name="f"):
         self.function_space = V
         self.name = name
+        self._dev = None
         arr = np.zeros(V.n, dtype=dtype) if values is None else np.array(values, dtype=dtype).reshape(V.n)
-        self.x = _X(arr)
+        self._x = _X(arr)
+
+    @classmethod
+    def from_device(cls, V, values_f64, name="f"):
+        """A real-valued field computed on the device (a coefficient builder's output): the host
+        array .x.array is only materialised when somebody asks for it."""
+        f = cls.__new__(cls)
+        f.function_space, f.name, f._dev, f._x = V, name, values_f64, None
+        return f
+
+    @property
+    def x(self):
+        if self._x is None:
+            self._x = _X(self._dev.cpu().numpy().astype(np.complex128))
+            self._dev = None               # the host copy is writable: it is the truth from now on
+        return self._x
 
     def copy(self):
+        if self._x is None:
+            return Function.from_device(self.function_space, self._dev.clone(), self.name)
         return Function(self.function_space, self.x.array.copy(), self.x.array.dtype, self.name)
 
     def real_device(self):
+        if self._x is None:
+            return self._dev
         return self.function_space.be.asarray(np.ascontiguousarray(self.x.array.real), dtype=f64)
 
     def interpolate(self, fn):
@@ -348,9 +408,10 @@ def assemble_AC(V: FunctionSpace, c):
     a = be.zeros(nnz, dtype=f64)
     cv = be.zeros(nnz, dtype=f64)
     ncol, ptr, order = m.cell_colors()
-    _lib.call("hx_assemble_AC", V.degree, m.n_cells, m.xd.data_ptr(), m.cellsd.data_ptr(), V.cell_dofs.data_ptr(),
-              cd.data_ptr(), int(dg0), ncol, ptr.ctypes.data_as(C.c_void_p), order.data_ptr(), indptr.data_ptr(),
-              indices.data_ptr(), a.data_ptr(), cv.data_ptr(), be.stream)
+    with phase("assembly"):
+        _lib.call("hx_assemble_AC", V.degree, m.n_cells, m.xd.data_ptr(), m.cellsd.data_ptr(), V.cell_dofs.data_ptr(),
+                  cd.data_ptr(), int(dg0), ncol, ptr.ctypes.data_as(C.c_void_p), order.data_ptr(), indptr.data_ptr(),
+                  indices.data_ptr(), a.data_ptr(), cv.data_ptr(), be.stream)
     return a, cv
 
 
@@ -406,14 +467,14 @@ def flame_left(V, h, scale, gm1_nodal=None, gm1_const=0.0, tag=None):
     if not h_dg0:
         hd = _p1_nodal(V, hd)
     out = be.zeros(V.n, dtype=f64)
-    ncol, ptr, order = m.cell_colors()
+    # tag given: only the cells carrying it are visited (colour-ordered like the full list)
+    ncol, ptr, order = m.cell_colors() if tag is None else m.tagged_cell_colors(tag)
     gd = None
     if gm1_nodal is not None:
         gd = _p1_nodal(V, be.asarray(gm1_nodal, dtype=f64))
     _lib.call("hx_flame_left", V.degree, m.n_cells, m.xd.data_ptr(), m.cellsd.data_ptr(), V.cell_dofs.data_ptr(),
               gd.data_ptr() if gd is not None else None, float(gm1_const), hd.data_ptr(), int(h_dg0), float(scale),
-              m.cell_tagsd.data_ptr() if tag is not None else None, int(tag if tag is not None else 0), ncol,
-              ptr.ctypes.data_as(C.c_void_p), order.data_ptr(), out.data_ptr(), be.stream)
+              None, 0, ncol, ptr.ctypes.data_as(C.c_void_p), order.data_ptr(), out.data_ptr(), be.stream)
     return out
 
 

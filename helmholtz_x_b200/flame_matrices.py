@@ -7,6 +7,7 @@ import torch
 from . import fem
 from .operators import LowRankMat, build_lowrank
 from .parameters_utils import gamma_function
+from .phases import phase
 from .solver_utils import info
 
 
@@ -114,10 +115,17 @@ class PointwiseFlameMatrix(FlameMatrix):
         self.subdomains = subdomains
 
     def _assemble_vectors(self, flame, point=None):
-        left = fem.flame_left(self.V, self._local(self.h), self.q_0 / self.u_b, gm1_const=self.gamma - 1, tag=flame)
+        if getattr(self, "_h_dev", None) is None:
+            # one upload of the heat-release field for all flames (a DG0 field has one value per cell)
+            self._h_dev = fem._field(self.V, self._local(self.h))[0]
+        left = fem.flame_left(self.V, self._h_dev, self.q_0 / self.u_b, gm1_const=self.gamma - 1, tag=flame)
         return self.indices_and_values(left)
 
     def assemble_submatrices(self, problem_type='direct'):
+        with phase("flame_vectors"):
+            self._assemble_submatrices(problem_type)
+
+    def _assemble_submatrices(self, problem_type):
         info("- Generating matrix D..")
         V = self.V
         pts = np.asarray(self.x_r, float).reshape(-1, 3)
@@ -152,6 +160,7 @@ class PointwiseFlameMatrix(FlameMatrix):
                     keep &= cell_dofs[flame] < self.part.n_own
                 rights.append((cell_dofs[flame][keep].astype(np.int32), vals[keep]))
             info("- Matrix contribution of flame " + str(flame) + " is computed.")
+        self._h_dev = None
         self._set(lefts, rights, problem_type)
         info("- Submatrix D is Assembled.")
 
@@ -177,7 +186,8 @@ class DistributedFlameMatrix(FlameMatrix):
         return self.indices_and_values(left), self.indices_and_values(right)
 
     def assemble_submatrices(self, problem_type='direct'):
-        left, right = self._assemble_vectors(problem_type)
+        with phase("flame_vectors"):
+            left, right = self._assemble_vectors(problem_type)
         info("- Generating matrix D..")
         self._set([left], [right], problem_type)
         info("- Submatrix D is Assembled.")

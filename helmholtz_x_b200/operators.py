@@ -17,6 +17,7 @@ from . import krylov
 from .amg import AMG
 from .backend import LowRank
 from .fem import _Vec
+from .phases import phase
 
 c128 = torch.complex128
 f64 = torch.float64
@@ -249,7 +250,8 @@ class OperatorSet:
             import time
             from .dist import DistHierarchy
             t0 = time.perf_counter()
-            self._hier = DistHierarchy(self.space, self.base, **self.amg_options)
+            with phase("amg_setup"):
+                self._hier = DistHierarchy(self.space, self.base, **self.amg_options)
             self._amg = self._hier.mg
             self.stats["amg_setups"] += 1
             self.stats["t_amg_setup"] += time.perf_counter() - t0
@@ -264,8 +266,9 @@ class OperatorSet:
             t0 = time.perf_counter()
             dm = self.space.diag_matrix
             B = dm(self.base["B"]) if self.base["B"] is not None else None
-            self._amg = AMG(self.space.local_be, dm(self.base["A"]), dm(self.base["C"]), B, self.space.dof_coords,
-                            **self.amg_options)
+            with phase("amg_setup"):
+                self._amg = AMG(self.space.local_be, dm(self.base["A"]), dm(self.base["C"]), B, self.space.dof_coords,
+                                **self.amg_options)
             self.stats["amg_setups"] += 1
             self.stats["t_amg_setup"] += time.perf_counter() - t0
         if self._amg is None:
@@ -273,7 +276,8 @@ class OperatorSet:
             B = pat(self.base["B"]) if self.base["B"] is not None else None
             import time
             t0 = time.perf_counter()
-            self._amg = AMG(self.be, pat(self.base["A"]), pat(self.base["C"]), B, self.space.dof_coords, **self.amg_options)
+            with phase("amg_setup"):
+                self._amg = AMG(self.be, pat(self.base["A"]), pat(self.base["C"]), B, self.space.dof_coords, **self.amg_options)
             self.be.synchronize()
             self.stats["amg_setups"] += 1
             self.stats["t_amg_setup"] += time.perf_counter() - t0
@@ -302,46 +306,47 @@ class ShiftedSolver:
         mg = ops.amg()
         st = getattr(ops, "_shift_state", None)
         if st is None or st["key"] != key:
-            t_shift0 = time.perf_counter()
-            use_bh = t.get("Bh", 0) != 0
-            P_values = ops.combine(t)
-            P = ops.space.matrix(P_values)
-            if hier is not None:
-                fine_vals = None                 # replicated global levels are combined from their own bases
-            else:
-                fine_vals = P_values if ops.part is None else P_values[ops.space.diag_sel].contiguous()
-            if use_bh:
-                # coarse B^H = conj(B_c): run the hierarchy on conjugated B
-                for L in mg.levels:
-                    if L.b is not None and not hasattr(L, "b_direct"):
-                        L.b_direct = L.b
-                        L.b_conj = torch.conj_physical(L.b)
-                for L in mg.levels:
-                    if L.b is not None:
-                        L.b = L.b_conj
-                mg.set_shift(t.get("A", 0), t.get("Bh", 0), t.get("C", 0), fine_values=fine_vals)
-                for L in mg.levels:
-                    if L.b is not None:
-                        L.b = L.b_direct
-            else:
-                mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=fine_vals)
-            Pop = mg.fine_operator() if (len(mg.levels) > 1 and ops.part is None) else P
-            if hier is not None:
-                hier.set_fine(P_values)
-            elif ops.part is not None:
-                ops.coarse().set_shift(t)
-            # ||P|| estimate for the backward-error test: 2 max|p_ij| (<= 2 ||P||_2; FEM rows give
-            # ||P||_inf of 2-3 max|p_ii|); the factor is immaterial against eta's decades
-            pmax = P_values.abs().max() if P_values.numel() else torch.zeros((), dtype=f64)
-            if ops.part is not None:
-                ops.part.all_reduce_max(pmax)
-            st = {"key": key, "P_values": P_values, "P": P, "Pop": Pop, "wood": {}, "anorm": 2.0 * float(pmax),
-                  "basis": krylov.ArnoldiBasis(be, ops.n, restart), "work": be.zeros(ops.n),
-                  "xc": be.zeros(ops.n), "r": be.zeros(ops.n),
-                  "zbasis": be.zeros(restart, ops.n) if getattr(mg, "single", False) else None}
-            ops._shift_state = st
-            ops.stats["shifts"] += 1
-            ops.stats["t_shift"] += time.perf_counter() - t_shift0
+            with phase("shift_setup"):
+                t_shift0 = time.perf_counter()
+                use_bh = t.get("Bh", 0) != 0
+                P_values = ops.combine(t)
+                P = ops.space.matrix(P_values)
+                if hier is not None:
+                    fine_vals = None                 # replicated global levels are combined from their own bases
+                else:
+                    fine_vals = P_values if ops.part is None else P_values[ops.space.diag_sel].contiguous()
+                if use_bh:
+                    # coarse B^H = conj(B_c): run the hierarchy on conjugated B
+                    for L in mg.levels:
+                        if L.b is not None and not hasattr(L, "b_direct"):
+                            L.b_direct = L.b
+                            L.b_conj = torch.conj_physical(L.b)
+                    for L in mg.levels:
+                        if L.b is not None:
+                            L.b = L.b_conj
+                    mg.set_shift(t.get("A", 0), t.get("Bh", 0), t.get("C", 0), fine_values=fine_vals)
+                    for L in mg.levels:
+                        if L.b is not None:
+                            L.b = L.b_direct
+                else:
+                    mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=fine_vals)
+                Pop = mg.fine_operator() if (len(mg.levels) > 1 and ops.part is None) else P
+                if hier is not None:
+                    hier.set_fine(P_values)
+                elif ops.part is not None:
+                    ops.coarse().set_shift(t)
+                # ||P|| estimate for the backward-error test: 2 max|p_ij| (<= 2 ||P||_2; FEM rows give
+                # ||P||_inf of 2-3 max|p_ii|); the factor is immaterial against eta's decades
+                pmax = P_values.abs().max() if P_values.numel() else torch.zeros((), dtype=f64)
+                if ops.part is not None:
+                    ops.part.all_reduce_max(pmax)
+                st = {"key": key, "P_values": P_values, "P": P, "Pop": Pop, "wood": {}, "anorm": 2.0 * float(pmax),
+                      "basis": krylov.ArnoldiBasis(be, ops.n, restart), "work": be.zeros(ops.n),
+                      "xc": be.zeros(ops.n), "r": be.zeros(ops.n),
+                      "zbasis": be.zeros(restart, ops.n) if getattr(mg, "single", False) else None}
+                ops._shift_state = st
+                ops.stats["shifts"] += 1
+                ops.stats["t_shift"] += time.perf_counter() - t_shift0
         self.st = st
         self.mg = mg
         self.P_values, self.P, self.Pop = st["P_values"], st["P"], st["Pop"]
@@ -372,6 +377,10 @@ class ShiftedSolver:
         return out
 
     def _solve_P(self, b, x):
+        with phase("inner_solve"):
+            return self._solve_P_timed(b, x)
+
+    def _solve_P_timed(self, b, x):
         import time
         t0 = time.perf_counter()
         info = {}
@@ -412,28 +421,29 @@ class ShiftedSolver:
         r_tot = sum(m.lr.r for m in self.lowrank)
         cache = self.st["wood"].get(wkey)
         if cache is None:
-            Zbase = be.zeros(r_tot, n)
-            u = be.zeros(n)
-            col = 0
-            for m in self.lowrank:
-                e = be.zeros(m.lr.r)
-                for f in range(m.lr.r):
-                    u.zero_()
-                    e.zero_()
-                    e[f] = 1.0
-                    be.lowrank_update(m.lr, e, 1.0, u)              # u = left_f
-                    self._solve_P(u, Zbase[col])
-                    col += 1
-            Sbase = np.zeros((r_tot, r_tot), complex)
-            row = 0
-            t = be.zeros(max(max(m.lr.r for m in self.lowrank), 1))
-            for m in self.lowrank:
-                for cz in range(r_tot):
-                    be.lowrank_dots(m.lr, Zbase[cz], t)
-                    Sbase[row:row + m.lr.r, cz] = t[:m.lr.r].cpu().numpy()
-                row += m.lr.r
-            cache = (Zbase, Sbase, t)
-            self.st["wood"] = {wkey: cache}                          # keep one entry: bounded memory
+            with phase("woodbury"):
+                Zbase = be.zeros(r_tot, n)
+                u = be.zeros(n)
+                col = 0
+                for m in self.lowrank:
+                    e = be.zeros(m.lr.r)
+                    for f in range(m.lr.r):
+                        u.zero_()
+                        e.zero_()
+                        e[f] = 1.0
+                        be.lowrank_update(m.lr, e, 1.0, u)              # u = left_f
+                        self._solve_P(u, Zbase[col])
+                        col += 1
+                Sbase = np.zeros((r_tot, r_tot), complex)
+                row = 0
+                t = be.zeros(max(max(m.lr.r for m in self.lowrank), 1))
+                for m in self.lowrank:
+                    for cz in range(r_tot):
+                        be.lowrank_dots(m.lr, Zbase[cz], t)
+                        Sbase[row:row + m.lr.r, cz] = t[:m.lr.r].cpu().numpy()
+                    row += m.lr.r
+                cache = (Zbase, Sbase, t)
+                self.st["wood"] = {wkey: cache}                          # keep one entry: bounded memory
         self.Zbase, Sbase, self._t = cache
         self.coefs = np.concatenate([np.full(m.lr.r, m.coef) for m in self.lowrank])
         self.S_inv = np.linalg.inv(np.eye(r_tot, dtype=complex) + Sbase * self.coefs[None, :])

@@ -194,8 +194,17 @@ int hx_dof_cell_fill(int64_t n_cells, int nd, const int32_t* cell_dofs, int n_do
 int hx_pattern_rows(int n_dofs, int nd, const int32_t* cell_dofs, const int32_t* adj_ptr, int32_t* adj_cells,
                     int32_t* row_nnz, const int32_t* indptr, int32_t* indices, int write_cols,
                     hx_stream_t stream);
-/* greedy colouring of cells so that cells of one colour share no vertex
- * (host integer preprocessing; arrays are HOST pointers). returns #colours or <0 */
+/* Colouring of cells (or facets) so that entities of one colour share no vertex, on the device:
+ * Jones-Plassmann rounds with fixed hashed priorities; decisions read only the state at the start of
+ * a round, so the result depends on the mesh alone (bitwise reproducible assembly).
+ * adj_ptr/adj_cells: vertex -> entity adjacency (hx_dof_cell_count / hx_dof_cell_fill with nd = nv);
+ * color_a (initialised to -1) and color_b ping-pong, `rounds` (even) rounds per call, result in
+ * color_a; *remaining_dev = entities still uncoloured (call again until 0).  -2 = more than 128 colours. */
+int hx_color_cells(int64_t n_cells, int nv, const int32_t* cells, const int32_t* adj_ptr,
+                   const int32_t* adj_cells, int32_t* color_a, int32_t* color_b, int rounds,
+                   uint64_t* remaining_dev, hx_stream_t stream);
+/* the same job as a host greedy first-fit (kept as the checker of the device colouring in tests;
+ * arrays are HOST pointers). returns #colours or <0 */
 int hx_color_cells_h(int64_t n_cells, int nv, const int32_t* cells_h, int n_nodes, int32_t* color_h);
 
 /* ------------------------------------------------------------------ K1 / K2 / K3
@@ -256,6 +265,56 @@ int hx_shape_derivative(int degree, int n_sel, const int32_t* sel, const double*
                         const double* c_nodal_f64, double* out_c128, hx_stream_t stream);
 /* |v|<tol -> 0 (flame_matrices.py:67-68; values are real) */
 int hx_threshold(int64_t n, double* v_f64, double tol, hx_stream_t stream);
+
+/* ------------------------------------------------------------------ multi-GPU (row e)
+ * Peer-memory data path for one process per GPU on one NVLink/NVSwitch node.  Replaces, on the
+ * per-iteration path, PETSc's VecScatter inside MatMult on an MPIAIJ matrix
+ * (helmholtz_x/petsc4py_utils.py:86,96 under mpirun) and the MPI_Allreduce inside
+ * VecDot / VecNorm / BVOrthogonalize (helmholtz_x/eigensolvers.py:62,113): the kernels below store
+ * straight into the neighbours' HBM and synchronise with sequence flags -- no NCCL call and no host
+ * round trip, so they can be captured in a CUDA graph with the kernels around them.
+ * (torch.distributed/NCCL remains the set-up plumbing.) */
+#define HX_PEER_MAX 15          /* neighbours of one rank (world <= 16) */
+#define HX_PEER_FLAG_KINDS 3    /* flag block of a rank: [HX_PEER_FLAG_KINDS][world] uint64 */
+
+/* hx_peer_alloc: cudaMalloc + zero fill + IPC handle (64 bytes) of a buffer other ranks may map;
+ * hx_peer_open maps a handle received from another process (peer access enabled lazily). */
+int hx_peer_alloc(int64_t bytes, void** ptr_out_h, unsigned char* handle64_h);
+int hx_peer_open(const unsigned char* handle64_h, void** ptr_out_h);
+int hx_peer_close(void* ptr);
+int hx_peer_free(void* ptr);
+
+/* one neighbour exchange of interface values (host descriptor, passed to the kernel by value) */
+typedef struct {
+    int32_t world, rank, n_nb, pad_;
+    int32_t nb_rank[HX_PEER_MAX + 1];  /* neighbour ranks */
+    int64_t send_ptr[HX_PEER_MAX + 1]; /* send_idx[send_ptr[i]..send_ptr[i+1]) goes to neighbour i */
+    const int32_t* send_idx;           /* device: local indices of the values to send */
+    void* dst[HX_PEER_MAX];            /* neighbour i's memory: start of the ghost segment this rank fills */
+    void* nb_flags[HX_PEER_MAX];       /* neighbour i's flag block (in its memory) */
+    void* my_flags;                    /* this rank's flag block */
+    void* chan_seq;                    /* device uint64[world]: exchanges completed per channel */
+    void* block_counter;               /* device uint32 (zero) */
+    int32_t* err;                      /* device int32: set non-zero when a wait timed out */
+} hx_peer_halo_desc;
+/* x_local[send_idx[..]] -> neighbours' ghost segments; returns (in stream order) when this rank's
+ * ghost values have arrived as well.  elem_bytes: 16 (complex128) or 8 (complex64). */
+int hx_peer_halo_exchange(const hx_peer_halo_desc* plan_h, const void* x_local, int elem_bytes, hx_stream_t stream);
+
+typedef struct {
+    int32_t world, rank;
+    int64_t slot_bytes;                /* capacity of one contribution */
+    void* slots[HX_PEER_MAX + 1];      /* rank q's slot area: [2][world][slot_bytes] */
+    void* flags[HX_PEER_MAX + 1];      /* rank q's flag block */
+    void* my_flags;
+    void* seq;                         /* device uint64: all-reduces completed */
+    void* block_counter;               /* device uint32[2] (zero) */
+    int32_t* err;
+} hx_peer_allreduce_desc;
+/* out[i] = sum over ranks of in[i], summed in rank order (bitwise identical on every rank).
+ * count doubles (is_f32=0) or floats (is_f32=1); in may alias out. */
+int hx_peer_allreduce(const hx_peer_allreduce_desc* ar_h, const void* in, void* out, int64_t count, int is_f32,
+                      hx_stream_t stream);
 
 #ifdef __cplusplus
 }
