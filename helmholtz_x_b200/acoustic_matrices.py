@@ -33,8 +33,7 @@ class AcousticMatrices:
             info("/\\ Temperature function is used for passive flame matrices.")
         else:
             self.c = parameter
-            self.gamma = self.c.copy()
-            self.gamma.x.array[:] = 1.4
+            self.gamma = self.c.copy().fill(1.4)
             info("\\/ Speed of sound function is used for passive flame matrices.")
 
         terms = []          # (tag, i/Z) of the impedance boundaries (acoustic_matrices.py:68-97)

@@ -370,6 +370,14 @@ class Function:
             return Function.from_device(self.function_space, self._dev.clone(), self.name)
         return Function(self.function_space, self.x.array.copy(), self.x.array.dtype, self.name)
 
+    def fill(self, value):
+        """Set every entry (without materialising the host array of a device-backed field)."""
+        if self._x is None:
+            self._dev.fill_(float(np.real(value)))
+        else:
+            self._x.array[:] = value
+        return self
+
     def real_device(self):
         if self._x is None:
             return self._dev

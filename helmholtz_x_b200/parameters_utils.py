@@ -133,15 +133,13 @@ def Q_volumetric(mesh, subdomains, Q_total, flame_tag=0, degree=0):
 
 
 def Q_multiple(mesh, subdomains, N_sector, degree=0):
-    """parameters_utils.py:228-247: DG0, 1/V_f on the cells tagged f.  Computed on the device (one
-    weighted bincount over the cell tags); the host array appears only if the caller reads it."""
+    """parameters_utils.py:228-247: DG0, 1/V_f on the cells tagged f.  Computed on the device (masked
+    sums, fixed reduction order); the host array appears only if the caller reads it."""
     import torch
     vol = mesh.volumes()
-    tags = mesh.cell_tagsd.long()
-    inside = (tags >= 0) & (tags < N_sector)
-    t = torch.where(inside, tags, torch.full_like(tags, N_sector))
-    vsum = torch.zeros(N_sector + 1, dtype=vol.dtype, device=vol.device)
-    vsum.index_add_(0, t, vol)
-    inv = torch.where(vsum > 0, 1.0 / vsum, torch.zeros_like(vsum))
-    inv[N_sector] = 0.0
-    return Function.from_device(DG0Space(mesh), inv[t].contiguous())
+    tags = mesh.cell_tagsd
+    q = torch.zeros_like(vol)
+    for flame in range(N_sector):
+        sel = tags == flame
+        q = torch.where(sel, 1.0 / vol[sel].sum(), q)
+    return Function.from_device(DG0Space(mesh), q)
