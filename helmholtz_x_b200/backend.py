@@ -88,6 +88,7 @@ class CudaBackend:
     supports_mixed = True        # complex64 kernels for the multigrid cycle
     supports_spgemm = True       # hx_spgemm_* for the multigrid set-up
     supports_graphs = True       # CUDA-graph capture of fixed launch sequences (the multigrid cycle)
+    supports_pipelining = True   # Hessenberg columns return through a pinned buffer on a copy stream
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():

@@ -10,13 +10,45 @@ The same code runs over gloo with the CPU test double (tests/test_dist_cpu.py).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from .backend import CsrMatrix
+from .peer import HaloExchanger, PeerGroup, transport
 
 c128 = torch.complex128
+
+
+def _gloo():
+    return dist.get_backend() == "gloo"
+
+
+def all_gather_tensors(bufs, t):
+    """dist.all_gather that also works for CUDA tensors over gloo (several ranks on one GPU in the tests)."""
+    if t.is_cuda and _gloo():
+        cb = [torch.zeros_like(b, device="cpu") for b in bufs]
+        dist.all_gather(cb, t.cpu())
+        for b, c in zip(bufs, cb):
+            b.copy_(c)
+    else:
+        dist.all_gather(bufs, t)
+
+
+def use_peer(t):
+    """Peer-memory transport for this tensor's collectives?  (CUDA + more than one rank + not switched off.)"""
+    return t.is_cuda and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and transport() == "peer"
+
+
+def all_reduce_sum_(t):
+    """In-place sum over ranks on the per-iteration path: one peer-memory kernel, or torch.distributed."""
+    if use_peer(t):
+        PeerGroup.get().allreduce_(t)
+    else:
+        dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t)
+    return t
 
 
 def world_info():
@@ -102,48 +134,20 @@ class Partition:
     def neighbours(self):
         return [q for q in range(self.world) if q != self.rank and (self.send_counts[q] or self.ghost_owner_counts[q])]
 
-    def _send_idx(self, device):
+    def exchanger(self, device):
         key = str(device)
         if key not in self._dev:
-            self._dev[key] = torch.as_tensor(self.send_idx_h, device=device)
+            send_idx = torch.as_tensor(self.send_idx_h, device=device)
+            self._dev[key] = HaloExchanger(self.world, self.rank, self.n_own, send_idx, self.send_counts,
+                                           self.ghost_owner_counts)
         return self._dev[key]
 
     def exchange(self, x_loc):
-        """Fill the ghost tail of x_loc (length n_loc, complex128) from the owners.
-        The packed send buffer and the grouped isend/irecv descriptors are cached per buffer,
-        so a repeated exchange costs one gather kernel + one grouped NCCL launch."""
-        if self.world == 1 or (self.n_ghost == 0 and self.send_idx_h.size == 0):
+        """Fill the ghost tail of x_loc (length n_loc) from the owners: one peer-memory kernel, or one
+        gather + one grouped send/recv (peer.HaloExchanger)."""
+        if self.world == 1:
             return x_loc
-        key = (x_loc.data_ptr(), x_loc.numel())
-        plan = self._plans.get(key) if hasattr(self, "_plans") else None
-        if plan is None:
-            if not hasattr(self, "_plans"):
-                self._plans = {}
-            if len(self._plans) > 16:
-                self._plans.clear()
-            sendbuf = torch.zeros(max(self.send_idx_h.size, 1), dtype=x_loc.dtype, device=x_loc.device)
-            sreal = torch.view_as_real(sendbuf)
-            ghost = torch.view_as_real(x_loc[self.n_own:])
-            ops, soff, roff = [], 0, 0
-            for q in range(self.world):
-                if q == self.rank:
-                    continue
-                ns, nr = int(self.send_counts[q]), int(self.ghost_owner_counts[q])
-                if ns:
-                    ops.append(dist.P2POp(dist.isend, sreal[soff:soff + ns], q))
-                if nr:
-                    ops.append(dist.P2POp(dist.irecv, ghost[roff:roff + nr], q))
-                soff += ns
-                roff += nr
-            plan = (sendbuf, ops, x_loc)          # keep x_loc alive: the plan is keyed by its address
-            self._plans[key] = plan
-        sendbuf, ops, _ = plan
-        if self.send_idx_h.size:
-            torch.index_select(x_loc, 0, self._send_idx(x_loc.device), out=sendbuf)
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        return x_loc
+        return self.exchanger(x_loc.device).exchange(x_loc)
 
     def all_reduce_max(self, t):
         """In-place maximum over ranks of a real device scalar / tensor."""
@@ -168,7 +172,7 @@ class Partition:
         pad = torch.zeros(mx, 2, dtype=torch.float64, device=x_own.device)
         pad[:self.n_own] = torch.view_as_real(x_own.contiguous())
         bufs = [torch.zeros_like(pad) for _ in range(self.world)]
-        dist.all_gather(bufs, pad)
+        all_gather_tensors(bufs, pad)
         ids = [None] * self.world
         dist.all_gather_object(ids, self.l2g[:self.n_own])
         out = np.zeros(self.n_global, complex)
@@ -182,20 +186,23 @@ class DistMatrix:
     """Owned rows of a distributed matrix: local CSR/SELL operator (n_own x n_loc)."""
     is_dist = True
 
-    def __init__(self, part: Partition, local, be_local):
+    def __init__(self, part: Partition, local, be_local, space=None):
         self.part, self.op = part, local
         self.n_rows = self.n_cols = part.n_own
         self.nnz = local.nnz
         self._xbuf = None
         self.be_local = be_local
+        self.space = space
 
     @property
     def shape(self):
         return (self.n_rows, self.n_cols)
 
     def xbuf(self):
+        """Input vector [owned | ghosts] of the local kernel; shared by all matrices of one space (it lives
+        in the space's peer arena when the halo travels over peer memory)."""
         if self._xbuf is None:
-            self._xbuf = self.be_local.zeros(self.part.n_loc)
+            self._xbuf = self.space.xbuf() if self.space is not None else self.be_local.zeros(self.part.n_loc)
         return self._xbuf
 
     def to_scipy_local(self):
@@ -211,6 +218,8 @@ class DistBackend:
         self.local, self.part = local, part
         self.device = local.device
         self.supports_sell = getattr(local, "supports_sell", False)
+        # the Hessenberg column can return through the pinned copy stream when no collective needs the host
+        self.supports_pipelining = getattr(local, "supports_pipelining", False) and transport() == "peer"
 
     def __getattr__(self, name):
         return getattr(self.local, name)
@@ -226,19 +235,19 @@ class DistBackend:
     def multi_dot(self, V, k, w, out, conj=True):
         self.local.multi_dot(V, k, w, out, conj)
         if self.part.world > 1:
-            dist.all_reduce(torch.view_as_real(out[:k]))
+            all_reduce_sum_(out[:k])
         return out
 
     def multi_axpy(self, V, k, h, w, hacc=None, nrm2=None):
         self.local.multi_axpy(V, k, h, w, hacc=hacc, nrm2=nrm2)
         if nrm2 is not None and self.part.world > 1:
-            dist.all_reduce(nrm2[:1])
+            all_reduce_sum_(nrm2[:1])
         return w
 
     def lowrank_dots(self, lr, x, t):
         self.local.lowrank_dots(lr, x, t)
         if self.part.world > 1:
-            dist.all_reduce(torch.view_as_real(t[:max(lr.r, 1)]))
+            all_reduce_sum_(t[:max(lr.r, 1)])
         return t
 
 
@@ -265,6 +274,24 @@ class DistSpace:
         dptr = torch.zeros(part.n_own + 1, dtype=torch.int64, device=ip.device)
         dptr[1:] = torch.cumsum(counts, 0)
         self._diag_pattern = (dptr.to(torch.int32).contiguous(), self._pattern[1][mask].contiguous())
+        self._xbuf = None
+        self._arena = None
+
+    def xbuf(self):
+        if self._xbuf is None:
+            n_loc = self.part.n_loc
+            if use_peer(self._pattern[0]):
+                grp = PeerGroup.get()
+                _, (mx,) = grp._all_min_max([n_loc])
+                self._arena = grp.lease(mx * 16 + 4096)
+                self._xbuf = self._arena.take(mx, c128, n_loc)
+            else:
+                self._xbuf = self.local_be.zeros(n_loc)
+        return self._xbuf
+
+    def __del__(self):
+        if getattr(self, "_arena", None) is not None:
+            self._arena.group.release(self._arena)
 
     def pattern(self):
         return self._pattern
@@ -274,7 +301,7 @@ class DistSpace:
 
     def matrix(self, values):
         local = CsrMatrix(self.part.n_own, self.part.n_loc, self._pattern[0], self._pattern[1], values)
-        return DistMatrix(self.part, local, self.local_be)
+        return DistMatrix(self.part, local, self.local_be, self)
 
     def diag_matrix(self, values):
         return CsrMatrix(self.part.n_own, self.part.n_own, self._diag_pattern[0], self._diag_pattern[1],
@@ -344,7 +371,7 @@ class CoarseCorrection:
         be = self.be
         be.spmv(self.R0, v, self.t)
         if self.part.world > 1:
-            dist.all_reduce(torch.view_as_real(self.t))
+            all_reduce_sum_(self.t)
         be.dense_gemv(self.inv, self.t, self.y)
         be.spmv(self.P0, self.y, x)
         return x
@@ -369,12 +396,12 @@ def _all_gather_rows(t, world):
     src = torch.view_as_real(t.contiguous()) if cplx else t.contiguous()
     n = torch.tensor([src.shape[0]], dtype=torch.int64, device=src.device)
     counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
+    all_gather_tensors(counts, n)
     counts = [int(c) for c in counts]
     pad = torch.zeros((max(counts),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     pad[:src.shape[0]] = src
     bufs = [torch.zeros_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)
+    all_gather_tensors(bufs, pad)
     out = torch.cat([b[:c] for b, c in zip(bufs, counts)])
     return torch.view_as_complex(out) if cplx else out
 
@@ -404,7 +431,7 @@ def _csr_transpose(M: CsrMatrix):
 
 class HaloPlan:
     """Exchange plan of one distributed level: `own` global ids (ascending) first, then the `ghost` ids
-    grouped by owner.  Same exchange step as Partition.exchange (one gather + one grouped send/recv)."""
+    grouped by owner.  Same exchange step as Partition.exchange (peer.HaloExchanger)."""
 
     def __init__(self, world, rank, own, ghost, owner):
         dev = own.device
@@ -429,43 +456,16 @@ class HaloPlan:
             send_counts[q] = int(mine.numel())
         self.send_counts = send_counts
         self.send_idx = torch.cat(send_idx) if send_idx else torch.zeros(0, dtype=torch.int64, device=dev)
-        self._plans = {}
+        self.ex = HaloExchanger(world, rank, self.n_own, self.send_idx, send_counts, self.ghost_owner_counts)
 
     @property
     def n_loc(self):
         return self.n_own + self.n_ghost
 
     def exchange(self, x_loc):
-        if self.world == 1 or (self.n_ghost == 0 and self.send_idx.numel() == 0):
+        if self.world == 1:
             return x_loc
-        key = (x_loc.data_ptr(), x_loc.numel())
-        plan = self._plans.get(key)
-        if plan is None:
-            if len(self._plans) > 16:
-                self._plans.clear()
-            sendbuf = torch.zeros(max(int(self.send_idx.numel()), 1), dtype=x_loc.dtype, device=x_loc.device)
-            sreal = torch.view_as_real(sendbuf)
-            ghost = torch.view_as_real(x_loc[self.n_own:])
-            ops, soff, roff = [], 0, 0
-            for q in range(self.world):
-                if q == self.rank:
-                    continue
-                ns, nr = int(self.send_counts[q]), int(self.ghost_owner_counts[q])
-                if ns:
-                    ops.append(dist.P2POp(dist.isend, sreal[soff:soff + ns], q))
-                if nr:
-                    ops.append(dist.P2POp(dist.irecv, ghost[roff:roff + nr], q))
-                soff += ns
-                roff += nr
-            plan = (sendbuf, ops, x_loc)
-            self._plans[key] = plan
-        sendbuf, ops, _ = plan
-        if self.send_idx.numel():
-            torch.index_select(x_loc, 0, self.send_idx, out=sendbuf)
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        return x_loc
+        return self.ex.exchange(x_loc)
 
 
 def _local_rows(M: CsrMatrix, own, g2l, n_loc):
@@ -566,14 +566,28 @@ class DistHierarchy:
             D.M_pat, D.M_pos = _local_rows(L.pattern, D.own, g2l, D.halo.n_loc)
             n_o, n_l = D.halo.n_own, D.halo.n_loc
             D.b = be.zeros(n_o, dtype=wd)
-            D.r = be.zeros(n_l, dtype=wd)
-            D.xa = be.zeros(n_l, dtype=wd)
-            D.xb = be.zeros(n_l, dtype=wd)
             D.dinv = be.zeros(n_o)
             if mg.w_from is not None:
                 D.xs = be.zeros(n_l, dtype=wd)
                 D.bs = be.zeros(n_o, dtype=wd)
             del D.need
+        # the vectors whose ghost tails the neighbours fill: in a peer arena when the halo travels over
+        # peer memory (sizes = maximum over ranks, so every rank computes the same offsets)
+        self._arena = None
+        n_locs = [D.halo.n_loc for D in self.dl]
+        if use_peer(ip):
+            grp = PeerGroup.get()
+            _, mx = grp._all_min_max(n_locs)
+            item = torch.empty(0, dtype=wd).element_size()
+            self._arena = grp.lease(sum(3 * (m_ * item + 256) for m_ in mx) + 4096)
+            for D, m_, n_l in zip(self.dl, mx, n_locs):
+                D.r, D.xa, D.xb = (self._arena.take(m_, wd, n_l) for _ in range(3))
+        else:
+            for D, n_l in zip(self.dl, n_locs):
+                D.r, D.xa, D.xb = be.zeros(n_l, dtype=wd), be.zeros(n_l, dtype=wd), be.zeros(n_l, dtype=wd)
+        self._graph = None
+        self.use_graph = (self._arena is not None and getattr(be, "supports_graphs", False)
+                          and os.environ.get("HX_AMG_GRAPH", "1") != "0")
         for l, D in enumerate(self.dl):
             L = mg.levels[l]
             if l + 1 < n_dist:
@@ -596,6 +610,7 @@ class DistHierarchy:
             D.dinv_w = D.dinv.to(self.wdtype) if self.single else D.dinv
             D.M = M.with_values(vals.to(self.wdtype)) if self.single else M
             D.omegas = self.mg.levels[l].omegas       # constant, or the level's Chebyshev roots of this shift
+        self._graph = None                            # the captured cycle points at the previous shift's operators
 
     def _sweeps(self, D, first_zero):
         be = self.be
@@ -633,7 +648,7 @@ class DistHierarchy:
             b1 = mg.levels[l + 1].b_
             be.spmv(D.R, D.r, b1)
             if self.part.world > 1:
-                dist.all_reduce(torch.view_as_real(b1))
+                all_reduce_sum_(b1)
             x1 = mg._cycle(l + 1, b1)
             if mg.w_from is not None and mg.w_from <= l + 1 < len(mg.levels) - 1:
                 Lc = mg.levels[l + 1]
@@ -645,9 +660,42 @@ class DistHierarchy:
             be.spmv(D.P, x1, D.xa, alpha=1.0, beta=1.0, y0=D.xa)
         self._sweeps(D, first_zero=False)
 
+    def __del__(self):
+        if getattr(self, "_arena", None) is not None:
+            self._arena.group.release(self._arena)
+
+    def _capture(self):
+        """Record one distributed cycle -- kernels, halo exchanges and all-reduces, all plain launches over
+        peer memory -- into a CUDA graph (input dl[0].b, output dl[0].xa)."""
+        be = self.be
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._cycle(0)                                       # eager pass: lazy buffers / plans exist before capture
+            n0 = be.launch_count()
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(capture_error_mode="thread_local")
+            try:
+                self._cycle(0)
+            finally:
+                g.capture_end()
+            self._graph_kernels = be.launch_count() - n0
+            be.add_launches(-self._graph_kernels)                # recorded, not run
+        cur.wait_stream(side)
+        self._graph = g
+        self._graph_x = self.dl[0].xa                            # the buffer roles after one cycle are fixed
+
     def apply(self, v, out):
         D = self.dl[0]
         D.b.copy_(v)
+        if self.use_graph:
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+            self.be.add_launches(self._graph_kernels)
+            out.copy_(self._graph_x[:D.halo.n_own])
+            return out
         self._cycle(0)
         out.copy_(D.xa[:D.halo.n_own])
         return out

@@ -24,7 +24,7 @@ class ArnoldiBasis:
         self._h1r = torch.view_as_real(self.h1)
         # one GPU: the Hessenberg column comes back through a pinned buffer on a copy stream, so the
         # caller can queue the next operator application before waiting for it
-        self.pipelined = getattr(be, "name", "") == "cuda" and getattr(be, "supports_graphs", False)
+        self.pipelined = getattr(be, "supports_pipelining", False)
         if self.pipelined:
             self._host = torch.empty(m + 2, dtype=c128).pin_memory()
             self._copy_stream = torch.cuda.Stream(device=be.device)

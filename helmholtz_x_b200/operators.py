@@ -242,9 +242,11 @@ class OperatorSet:
         return self._coarse
 
     def hierarchy(self):
-        """Row-distributed multigrid cycle (dist.DistHierarchy), HX_DIST_HIERARCHY=1; None otherwise."""
+        """Row-distributed multigrid cycle (dist.DistHierarchy): the multi-GPU default -- the cycle is the
+        single-GPU cycle up to summation order, so the iteration count does not depend on the number of
+        ranks.  HX_DIST_HIERARCHY=0: two-level Schwarz (global coarse correction + rank-local cycles)."""
         import os
-        if self.part is None or os.environ.get("HX_DIST_HIERARCHY", "0") != "1":
+        if self.part is None or os.environ.get("HX_DIST_HIERARCHY", "1") != "1":
             return None
         if getattr(self, "_hier", None) is None:
             import time
