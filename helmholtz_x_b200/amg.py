@@ -139,7 +139,7 @@ W_AUTO_MIN_ROWS = 3_000_000
 class AMG:
     def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=16,
                  coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=250000, precision="single",
-                 w_from=None, smoother=None):
+                 w_from=None, smoother=None, w_to=None):
         """A, C real-valued, B complex or None -- all on ONE shared fine pattern.
         precision="single": the V-cycle (smoother, residual, transfers) runs in complex64 --
         it is only a preconditioner; GMRES and everything outside stay complex128."""
@@ -168,10 +168,13 @@ class AMG:
             if env == "auto":
                 w_from = 1 if A.n_rows >= W_AUTO_MIN_ROWS else None
             elif env not in ("off", ""):
-                w_from = int(env)
+                # "<from>" or "<from>:<to>": levels from..to (inclusive) are visited twice per visit of their parent
+                lo, _, hi = env.partition(":")
+                w_from, w_to = int(lo), (int(hi) if hi else w_to)
         elif w_from == "off":
             w_from = None
         self.w_from = w_from
+        self.w_to = w_to if w_to is not None else 10 ** 6
         self.native_min_rows = 20000
         # the V-cycle is a fixed sequence of ~25 small launches on fixed buffers: captured once per
         # shift in a CUDA graph and replayed (HX_AMG_GRAPH=0 launches it kernel by kernel)
@@ -463,7 +466,7 @@ class AMG:
         Lc = self.levels[i + 1]
         be.spmv(L.R, L.r, Lc.b_)
         xc = self._cycle(i + 1, Lc.b_)
-        if self.w_from is not None and self.w_from <= i + 1 < len(self.levels) - 1:
+        if self.w_from is not None and self.w_from <= i + 1 <= self.w_to and i + 1 < len(self.levels) - 1:
             # second visit: the cycle applied to the coarse residual corrects xc
             Lc.xs.copy_(xc)
             Lc.bs.copy_(Lc.b_)

@@ -634,7 +634,7 @@ class DistHierarchy:
             D.halo.exchange(D.r)
             be.spmv(D.R, D.r, Dn.b)
             self._cycle(l + 1)
-            if mg.w_from is not None and mg.w_from <= l + 1:
+            if mg.w_from is not None and mg.w_from <= l + 1 <= mg.w_to:
                 # W-cycle: second visit of the (distributed) coarse level on its residual
                 Dn.xs.copy_(Dn.xa)
                 Dn.bs.copy_(Dn.b)
@@ -650,7 +650,7 @@ class DistHierarchy:
             if self.part.world > 1:
                 all_reduce_sum_(b1)
             x1 = mg._cycle(l + 1, b1)
-            if mg.w_from is not None and mg.w_from <= l + 1 < len(mg.levels) - 1:
+            if mg.w_from is not None and mg.w_from <= l + 1 <= mg.w_to and l + 1 < len(mg.levels) - 1:
                 Lc = mg.levels[l + 1]
                 Lc.xs.copy_(x1)
                 Lc.bs.copy_(b1)

@@ -69,6 +69,47 @@ def normalize_eigenvector(mesh, obj, i, absolute=False, degree=1, which='right',
     return omega, p_normalized
 
 
+class _VectorSpace:
+    """Blocked (x, y, z interleaved) P1 vector space: what velocity_eigenvector's result lives in."""
+
+    def __init__(self, mesh):
+        self.mesh, self.degree, self.bs = mesh, 1, 3
+        self.n = 3 * mesh.n_nodes
+        self.be = mesh.be
+
+
+def velocity_eigenvector(mesh, p, omega, rho, degree=1, normalize=True, absolute=False):
+    """u = grad(p) / (i omega rho) interpolated into the P1 vector space (eigenvectors.py:65-123).
+    Post-processing next to the hot path, done on the host: the gradient of a P1 field is constant per
+    cell and DOLFINx's interpolation leaves every vertex with the value of the last cell that holds it;
+    normalised so that int u . conj(u) dx = 1.  P1 pressure fields only."""
+    if degree != 1:
+        raise NotImplementedError("velocity_eigenvector: degree 1 only")
+    x, cells = mesh.x, mesh.cells.astype(np.int64)
+    pv = np.asarray(p.x.array)[:mesh.n_nodes]
+    e = x[cells[:, 1:]] - x[cells[:, :1]]                              # (nc, 3, 3) edge vectors
+    dp = pv[cells[:, 1:]] - pv[cells[:, :1]]                           # (nc, 3)
+    grad = np.linalg.solve(e.astype(complex), dp[:, :, None])[:, :, 0]  # e @ grad = dp
+    last = np.zeros(mesh.n_nodes, np.int64)
+    np.maximum.at(last, cells.ravel(), np.repeat(np.arange(len(cells)), 4))
+    u = grad[last]
+    if isinstance(rho, Function):
+        u = u / np.asarray(rho.x.array)[:mesh.n_nodes, None]
+        u = u / (1j * omega)
+    else:
+        u = u / (1j * omega * rho)
+    if normalize:
+        vol = np.abs(np.linalg.det(e)) / 6.0
+        uc = u[cells]                                                   # (nc, 4, 3)
+        integrand = (np.abs(uc) ** 2).sum(axis=(1, 2)) + (np.abs(uc.sum(axis=1)) ** 2).sum(axis=1)
+        u = u / np.sqrt(float((vol / 20.0 * integrand).sum()))
+    if absolute:
+        mag = np.sqrt((u ** 2).sum(axis=1))
+        u = np.abs(u) / np.abs(mag).max()
+    out = Function(_VectorSpace(mesh), u.reshape(-1), name="U")
+    return out
+
+
 def normalize_adjoint(omega_dir, p_dir, p_adj, matrices, D=None):
     """p_adj <- p_adj / (p_adj . dL/domega p_dir) with the reference's dot convention
     (eigenvectors.py:125-177)."""

@@ -97,9 +97,10 @@ class Mesh:
             return None
         if self._part is None:
             import os
-            part = hxdist.Partition(self.x, self.cells, world, rank, os.environ.get("HX_PARTITION", "morton"), self.facets)
-            part.local_mesh = Mesh(self.x[part.l2g], part.local_cells, self.cell_tags[part.cell_ids], part.local_facets,
-                                   self.facet_tags[part.facet_ids], backend=self.be)
+            with phase("partition"):
+                part = hxdist.Partition(self.x, self.cells, world, rank, os.environ.get("HX_PARTITION", "morton"), self.facets)
+                part.local_mesh = Mesh(self.x[part.l2g], part.local_cells, self.cell_tags[part.cell_ids], part.local_facets,
+                                       self.facet_tags[part.facet_ids], backend=self.be)
             self._part = part
         return self._part
 

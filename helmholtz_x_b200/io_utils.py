@@ -81,17 +81,19 @@ class XDMFReader:
 def xdmf_writer(name, mesh, function):
     """Write mesh + P1 function as XDMF/HDF5 with DOLFINx's dataset layout
     (/Mesh/Grid/{geometry,topology}, /Function/{real_,imag_}<name>/0; io_utils.py:40-60)."""
-    vals = np.asarray(function.x.array)[:mesh.n_nodes]
+    bs = getattr(function.function_space, "bs", 1)            # 3: blocked vector field (velocity_eigenvector)
+    vals = np.asarray(function.x.array)[:mesh.n_nodes * bs]
     fname = function.name
     h5 = os.path.basename(name) + ".h5"
     write_h5(name + ".h5", {
         "/Mesh/Grid/geometry": mesh.x, "/Mesh/Grid/topology": mesh.cells.astype(np.int64),
-        f"/Function/real_{fname}/0": np.real(vals).reshape(-1, 1).astype(np.float64),
-        f"/Function/imag_{fname}/0": np.imag(vals).reshape(-1, 1).astype(np.float64)})
+        f"/Function/real_{fname}/0": np.real(vals).reshape(-1, bs).astype(np.float64),
+        f"/Function/imag_{fname}/0": np.imag(vals).reshape(-1, bs).astype(np.float64)})
     n, nc = mesh.n_nodes, mesh.n_cells
+    kind = "Scalar" if bs == 1 else "Vector"
 
     def attr(part):
-        return (f'<Attribute Name="{part}_{fname}" AttributeType="Scalar" Center="Node"><DataItem Dimensions="{n} 1" '
+        return (f'<Attribute Name="{part}_{fname}" AttributeType="{kind}" Center="Node"><DataItem Dimensions="{n} {bs}" '
                 f'Format="HDF">{h5}:/Function/{part}_{fname}/0</DataItem></Attribute>')
     with open(name + ".xdmf", "w") as fh:
         fh.write(f'<Xdmf Version="3.0"><Domain><Grid Name="Grid" GridType="Uniform">'
