@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-DEFAULT_DOFS = int(os.environ.get("HX_BENCH_DOFS", 4_000_000))
+DEFAULT_DOFS = int(os.environ.get("HX_BENCH_DOFS", 5_000_000))
 # one extra step at the size BASELINE's target is quoted on, measured in the same run (N=1 only)
 RECORD_DOFS = int(os.environ.get("HX_BENCH_RECORD_DOFS", 10_000_000))
 # size at which BOTH arms run (the CPU oracle's sparse LU takes ~10-30 s there)
@@ -253,7 +253,7 @@ def _omega_reference(dofs):
     with open(path) as fh:
         table = json.load(fh)
     v = table.get(str(int(dofs)))
-    return complex(v[0], v[1]) if v else None
+    return complex(v[0], v[1]) if isinstance(v, list) else None
 
 
 def _sell_traffic(n, nnz):

@@ -80,11 +80,11 @@ class AcousticMatrices:
                 raise NotImplementedError("multi-GPU runs support degree 1 (dof = mesh node) in this round")
             from .dist import DistSpace
             Vasm = fem.functionspace(part.local_mesh, ("Lagrange", 1))
-            cvals = np.real(self.c.x.array)
+            cvals = self.c.real_device()                  # restricted on the device, no host round trip
             if isinstance(self.c.function_space, fem.DG0Space):
-                c_asm = fem.Function(fem.DG0Space(part.local_mesh), part.restrict_cell(cvals), dtype=np.float64)
+                c_asm = fem.Function.from_device(fem.DG0Space(part.local_mesh), part.restrict_cell(cvals))
             else:
-                c_asm = fem.Function(Vasm, part.restrict_nodal(cvals[:mesh.n_nodes]), dtype=np.float64)
+                c_asm = fem.Function.from_device(Vasm, part.restrict_nodal(cvals[:mesh.n_nodes]))
             bc_dofs = [part.g2l[d][part.g2l[d] >= 0] for d in bc_dofs]
         with phase("assembly_fields"):
             a_vals, c_vals = fem.assemble_AC(Vasm, c_asm)

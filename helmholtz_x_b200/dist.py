@@ -69,63 +69,88 @@ def morton_keys_np(x, bits=16):
 
 
 class Partition:
-    """Node ownership + this rank's sub-mesh numbering + the halo exchange plan."""
+    """Node ownership + this rank's sub-mesh numbering + the halo exchange plan.  Integer work on the
+    device the mesh lives on (torch; the CPU tests run the same code on CPU tensors); the host (numpy)
+    views the drivers' host-side code needs -- l2g, g2l, cell_ids, ... -- are materialised on first use."""
+
+    _HOST_VIEWS = ("owner", "pos", "cell_ids", "l2g", "g2l", "local_cells", "facet_ids", "local_facets")
 
     def __init__(self, x, cells, world, rank, ordering="input", facets=None):
-        n = x.shape[0]
-        self.world, self.rank, self.n_global = world, rank, n
+        x = torch.as_tensor(x)
+        dev = x.device
+        cells = torch.as_tensor(cells).to(dev).long()
+        n = int(x.shape[0])
+        self.world, self.rank, self.n_global, self.device = world, rank, n, dev
+        ar = torch.arange(n, device=dev)
         if ordering == "morton":
-            perm = np.argsort(morton_keys_np(x), kind="stable")
+            from .amg import morton_order
+            perm = morton_order(x.to(torch.float64))
         else:
-            perm = np.arange(n)
-        owner = np.empty(n, np.int32)
-        owner[perm] = (np.arange(n, dtype=np.int64) * world // n).astype(np.int32)
-        self.owner = owner
-        pos = np.empty(n, np.int64)
-        pos[perm] = np.arange(n, dtype=np.int64)
-        self.pos = pos                                  # rank of every node along the locality ordering
-        own = np.flatnonzero(owner == rank)
-        cell_mask = (owner[cells] == rank).any(axis=1)
-        self.cell_ids = np.flatnonzero(cell_mask)
+            perm = ar
+        owner = torch.empty(n, dtype=torch.int64, device=dev)
+        owner[perm] = ar * world // n
+        pos = torch.empty(n, dtype=torch.int64, device=dev)
+        pos[perm] = ar                                   # rank of every node along the locality ordering
+        own = torch.nonzero(owner == rank).reshape(-1)
+        cell_mask = (owner[cells] == rank).any(dim=1)
+        cell_ids = torch.nonzero(cell_mask).reshape(-1)
         lc = cells[cell_mask]
-        nodes = np.unique(lc)
+        nodes = torch.unique(lc)
         ghost = nodes[owner[nodes] != rank]
-        ghost = ghost[np.lexsort((ghost, owner[ghost]))]            # grouped by owner, ascending id
-        self.n_own, self.n_ghost = len(own), len(ghost)
-        self.l2g = np.concatenate([own, ghost]).astype(np.int64)
-        g2l = np.full(n, -1, np.int64)
-        g2l[self.l2g] = np.arange(len(self.l2g))
-        self.g2l = g2l
-        self.local_cells = g2l[lc].astype(np.int32)
+        ghost = ghost[torch.sort(owner[ghost] * n + ghost).indices]          # grouped by owner, ascending id
+        self.n_own, self.n_ghost = int(own.numel()), int(ghost.numel())
+        l2g = torch.cat([own, ghost])
+        g2l = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        g2l[l2g] = torch.arange(l2g.numel(), device=dev)
+        self._d = {"owner": owner, "pos": pos, "cell_ids": cell_ids, "l2g": l2g, "g2l": g2l,
+                   "local_cells": g2l[lc].to(torch.int32).contiguous()}
         if facets is not None and len(facets):
-            fmask = (owner[facets] == rank).any(axis=1)
-            self.facet_ids = np.flatnonzero(fmask)
-            self.local_facets = g2l[facets[fmask]].astype(np.int32)
-            assert self.local_facets.min(initial=0) >= 0
+            fac = torch.as_tensor(facets).to(dev).long()
+            fmask = (owner[fac] == rank).any(dim=1)
+            self._d["facet_ids"] = torch.nonzero(fmask).reshape(-1)
+            self._d["local_facets"] = g2l[fac[fmask]].to(torch.int32).contiguous()
+            assert int(self._d["local_facets"].min()) >= 0 if self._d["local_facets"].numel() else True
         else:
-            self.facet_ids = np.zeros(0, np.int64)
-            self.local_facets = np.zeros((0, 3), np.int32)
+            self._d["facet_ids"] = torch.zeros(0, dtype=torch.int64, device=dev)
+            self._d["local_facets"] = torch.zeros((0, 3), dtype=torch.int32, device=dev)
+        self._h = {}
         # ---- halo plan: who needs which of my rows --------------------------------------
-        self.ghost_owner_counts = np.bincount(owner[ghost], minlength=world)
+        self.ghost_owner_counts = torch.bincount(owner[ghost], minlength=world).cpu().numpy().astype(np.int64)
         if world > 1:
-            all_ghosts = [None] * world
-            dist.all_gather_object(all_ghosts, ghost.astype(np.int64))
-            all_own_counts = [None] * world
-            dist.all_gather_object(all_own_counts, int(self.n_own))
+            counts = _all_gather_rows(torch.tensor([self.n_ghost, self.n_own], dtype=torch.int64, device=dev).view(1, 2), world).cpu().numpy()
+            allg = _all_gather_rows(ghost, world)
         else:
-            all_ghosts, all_own_counts = [ghost], [self.n_own]
-        self.own_counts = np.array(all_own_counts, np.int64)
+            counts, allg = np.array([[self.n_ghost, self.n_own]]), ghost
+        self.own_counts = counts[:, 1].astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(counts[:, 0])])
         send_idx, send_counts = [], np.zeros(world, np.int64)
         for q in range(world):
             if q == rank:
                 continue
-            gq = all_ghosts[q]
+            gq = allg[int(off[q]):int(off[q + 1])]
             mine = gq[owner[gq] == rank]                              # in q's ghost order
             send_idx.append(g2l[mine])
-            send_counts[q] = len(mine)
+            send_counts[q] = int(mine.numel())
         self.send_counts = send_counts
-        self.send_idx_h = np.concatenate(send_idx).astype(np.int64) if send_idx else np.zeros(0, np.int64)
+        self.send_idx = torch.cat(send_idx) if send_idx else torch.zeros(0, dtype=torch.int64, device=dev)
         self._dev = {}
+        self._all_ids = None
+
+    def dev(self, name):
+        """Device tensor of one of the index arrays (owner, pos, cell_ids, l2g, g2l, local_cells, ...)."""
+        return self._d[name]
+
+    def __getattr__(self, name):
+        if name in Partition._HOST_VIEWS:
+            h = self.__dict__["_h"]
+            if name not in h:
+                h[name] = self.__dict__["_d"][name].cpu().numpy()
+            return h[name]
+        raise AttributeError(name)
+
+    @property
+    def send_idx_h(self):
+        return self.send_idx.cpu().numpy()
 
     @property
     def n_loc(self):
@@ -137,8 +162,7 @@ class Partition:
     def exchanger(self, device):
         key = str(device)
         if key not in self._dev:
-            send_idx = torch.as_tensor(self.send_idx_h, device=device)
-            self._dev[key] = HaloExchanger(self.world, self.rank, self.n_own, send_idx, self.send_counts,
+            self._dev[key] = HaloExchanger(self.world, self.rank, self.n_own, self.send_idx.to(device), self.send_counts,
                                            self.ghost_owner_counts)
         return self._dev[key]
 
@@ -157,9 +181,14 @@ class Partition:
 
     # ---- global <-> distributed host helpers -------------------------------------------
     def restrict_nodal(self, arr):
+        """Values at this rank's local (owned + ghost) nodes; device tensor in -> device tensor out."""
+        if torch.is_tensor(arr):
+            return arr[self._d["l2g"].to(arr.device)].contiguous()
         return np.asarray(arr)[self.l2g]
 
     def restrict_cell(self, arr):
+        if torch.is_tensor(arr):
+            return arr[self._d["cell_ids"].to(arr.device)].contiguous()
         return np.asarray(arr)[self.cell_ids]
 
     def gather_global(self, x_own):
@@ -173,8 +202,11 @@ class Partition:
         pad[:self.n_own] = torch.view_as_real(x_own.contiguous())
         bufs = [torch.zeros_like(pad) for _ in range(self.world)]
         all_gather_tensors(bufs, pad)
-        ids = [None] * self.world
-        dist.all_gather_object(ids, self.l2g[:self.n_own])
+        if getattr(self, "_all_ids", None) is None:           # static per partition
+            ids = [None] * self.world
+            dist.all_gather_object(ids, self.l2g[:self.n_own])
+            self._all_ids = ids
+        ids = self._all_ids
         out = np.zeros(self.n_global, complex)
         for q in range(self.world):
             v = bufs[q][:int(self.own_counts[q])].cpu().numpy()
@@ -303,6 +335,19 @@ class DistSpace:
         local = CsrMatrix(self.part.n_own, self.part.n_loc, self._pattern[0], self._pattern[1], values)
         return DistMatrix(self.part, local, self.local_be, self)
 
+    def matrix_sell(self, values):
+        """The owned rows in SELL-32 (the fine-level SpMV format of the single-GPU path) when the block is
+        large enough to pay; None otherwise."""
+        be = self.local_be
+        if not getattr(be, "supports_sell", False) or self.part.n_own < 250000:
+            return None
+        from .sell import SellMatrix, SellPattern
+        if getattr(self, "_sellp", None) is None:
+            self._sellp = SellPattern(be, self._pattern[0], self._pattern[1], self.part.n_own, self.part.n_loc)
+            self._sell_vals = be.empty(max(self._sellp.total, 1))
+        local = SellMatrix(self._sellp, self._sellp.values_from_csr(values, out=self._sell_vals))
+        return DistMatrix(self.part, local, be, self)
+
     def diag_matrix(self, values):
         return CsrMatrix(self.part.n_own, self.part.n_own, self._diag_pattern[0], self._diag_pattern[1],
                          values[self.diag_sel].contiguous())
@@ -323,7 +368,7 @@ class CoarseCorrection:
         dev = space._pattern[0].device
         nc = int(min(nc, max(part.n_global // 8, 1)))
         self.nc = nc
-        agg_loc = torch.as_tensor(part.pos[part.l2g] * nc // part.n_global, device=dev)
+        agg_loc = (part.dev("pos")[part.dev("l2g")] * nc // part.n_global).to(dev)
         n_own = part.n_own
         ip, ix = space._pattern
         rows = torch.repeat_interleave(torch.arange(n_own, device=dev), (ip[1:] - ip[:-1]).long())
@@ -507,7 +552,7 @@ class DistHierarchy:
         ip, ix = space._pattern
         dev = ip.device
         n_own, ng = part.n_own, part.n_global
-        l2g = torch.as_tensor(part.l2g, device=dev)
+        l2g = part.dev("l2g").to(dev)
         rows_loc = torch.repeat_interleave(torch.arange(n_own, device=dev), (ip[1:] - ip[:-1]).long())
         key = _all_gather_rows(l2g[rows_loc] * ng + l2g[ix.long()], world)
         order = torch.sort(key).indices
@@ -529,7 +574,7 @@ class DistHierarchy:
         if nlev < 2:
             raise ValueError("the distributed cycle needs at least two levels")
         # ---- ownership per level: a coarse dof belongs to the lowest rank owning one of its members
-        owners = [torch.as_tensor(part.owner.astype(np.int64), device=dev)]
+        owners = [part.dev("owner").to(dev)]
         n_dist = 1
         for l in range(1, nlev - 1):
             if mg.levels[l].n < min_rows * world:
@@ -567,6 +612,11 @@ class DistHierarchy:
             n_o, n_l = D.halo.n_own, D.halo.n_loc
             D.b = be.zeros(n_o, dtype=wd)
             D.dinv = be.zeros(n_o)
+            D.sellp = None
+            if mg.sell_min_rows is not None and n_o >= mg.sell_min_rows:
+                from .sell import SellPattern
+                D.sellp = SellPattern(be, D.M_pat.indptr, D.M_pat.indices, n_o, n_l)
+                D.sell_vals = be.empty(max(D.sellp.total, 1), dtype=wd)
             if mg.w_from is not None:
                 D.xs = be.zeros(n_l, dtype=wd)
                 D.bs = be.zeros(n_o, dtype=wd)
@@ -608,7 +658,11 @@ class DistHierarchy:
             M = D.M_pat.with_values(vals)
             be.diag_inv(M, D.dinv)
             D.dinv_w = D.dinv.to(self.wdtype) if self.single else D.dinv
-            D.M = M.with_values(vals.to(self.wdtype)) if self.single else M
+            if D.sellp is not None:
+                from .sell import SellMatrix
+                D.M = SellMatrix(D.sellp, D.sellp.values_from_csr(vals, out=D.sell_vals), variant=2 if (self.single and l == 0) else 0)
+            else:
+                D.M = M.with_values(vals.to(self.wdtype)) if self.single else M
             D.omegas = self.mg.levels[l].omegas       # constant, or the level's Chebyshev roots of this shift
         self._graph = None                            # the captured cycle points at the previous shift's operators
 

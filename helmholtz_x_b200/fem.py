@@ -47,9 +47,13 @@ class _Topology:
 
 
 class _Geometry:
-    def __init__(self, x):
-        self.x = x
+    def __init__(self, mesh):
+        self._mesh = mesh
         self.dim = 3
+
+    @property
+    def x(self):
+        return self._mesh.x
 
 
 class MeshTags:
@@ -64,22 +68,31 @@ class MeshTags:
 
 
 class Mesh:
-    """Tetrahedral mesh; arrays live on the host (numpy) and on the device (torch)."""
+    """Tetrahedral mesh.  Every array exists on the device (.xd, .cellsd, .cell_tagsd, .facetsd) and on
+    the host (.x, .cells, .cell_tags, .facets, .facet_tags as numpy).  The constructor takes either: numpy
+    arrays are uploaded, device tensors (the per-rank sub-meshes of a multi-GPU run are cut on the device)
+    are kept and their host copies appear only when somebody reads them."""
+
+    _LAZY = {"x": "xd", "cells": "cellsd", "cell_tags": "cell_tagsd", "facets": "facetsd", "facet_tags": "facet_tagsd"}
 
     def __init__(self, x, cells, cell_tags=None, facets=None, facet_tags=None, backend=None):
-        self.be = backend or default_backend()
-        self.x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
-        self.cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 4)
-        self.n_nodes, self.n_cells = self.x.shape[0], self.cells.shape[0]
-        self.cell_tags = np.zeros(self.n_cells, np.int32) if cell_tags is None else np.asarray(cell_tags, np.int32)
-        self.facets = np.zeros((0, 3), np.int32) if facets is None else np.ascontiguousarray(facets, np.int32).reshape(-1, 3)
-        self.facet_tags = np.zeros(len(self.facets), np.int32) if facet_tags is None else np.asarray(facet_tags, np.int32)
-        be = self.be
-        self.xd = be.asarray(self.x, dtype=f64)
-        self.cellsd = be.asarray(self.cells, dtype=i32)
-        self.cell_tagsd = be.asarray(self.cell_tags, dtype=i32)
-        self.facetsd = be.asarray(self.facets, dtype=i32)
-        self.geometry = _Geometry(self.x)
+        self.be = be = backend or default_backend()
+        self._host = {}
+
+        def both(name, a, dtype_np, dtype_t, shape):
+            if torch.is_tensor(a):
+                return a.to(be.device).to(dtype_t).reshape(shape).contiguous()
+            h = np.ascontiguousarray(a, dtype=dtype_np).reshape(shape)
+            self._host[name] = h
+            return be.asarray(h, dtype=dtype_t)
+        self.xd = both("x", x, np.float64, f64, (-1, 3))
+        self.cellsd = both("cells", cells, np.int32, i32, (-1, 4))
+        self.n_nodes, self.n_cells = int(self.xd.shape[0]), int(self.cellsd.shape[0])
+        self.cell_tagsd = both("cell_tags", np.zeros(self.n_cells, np.int32) if cell_tags is None else cell_tags, np.int32, i32, (-1,))
+        self.facetsd = both("facets", np.zeros((0, 3), np.int32) if facets is None else facets, np.int32, i32, (-1, 3))
+        self.facet_tagsd = both("facet_tags", np.zeros(int(self.facetsd.shape[0]), np.int32) if facet_tags is None else facet_tags,
+                                np.int32, i32, (-1,))
+        self.geometry = _Geometry(self)
         self.topology = _Topology(3)
         self._spaces = {}
         self._cell_colors = None
@@ -87,6 +100,15 @@ class Mesh:
         self._volumes = None
         self._facet_cell = None
         self._part = None
+
+    def __getattr__(self, name):
+        lazy = Mesh._LAZY.get(name)
+        if lazy is None:
+            raise AttributeError(name)
+        host = self.__dict__["_host"]
+        if name not in host:
+            host[name] = self.__dict__[lazy].cpu().numpy()
+        return host[name]
 
     def partition(self):
         """Row partition of this mesh over the process group (dist.Partition) with the
@@ -98,9 +120,9 @@ class Mesh:
         if self._part is None:
             import os
             with phase("partition"):
-                part = hxdist.Partition(self.x, self.cells, world, rank, os.environ.get("HX_PARTITION", "morton"), self.facets)
-                part.local_mesh = Mesh(self.x[part.l2g], part.local_cells, self.cell_tags[part.cell_ids], part.local_facets,
-                                       self.facet_tags[part.facet_ids], backend=self.be)
+                part = hxdist.Partition(self.xd, self.cellsd, world, rank, os.environ.get("HX_PARTITION", "morton"), self.facetsd)
+                part.local_mesh = Mesh(self.xd[part.dev("l2g")], part.dev("local_cells"), self.cell_tagsd[part.dev("cell_ids")],
+                                       part.dev("local_facets"), self.facet_tagsd[part.dev("facet_ids")], backend=self.be)
             self._part = part
         return self._part
 

@@ -61,11 +61,11 @@ class FlameMatrix:
         """Coefficient restricted to this rank's sub-mesh (identity on one GPU)."""
         if self.part is None or not isinstance(f, fem.Function):
             return f
-        vals = np.real(f.x.array)
+        vals = f.real_device()                            # restricted on the device, no host round trip
         if isinstance(f.function_space, fem.DG0Space):
-            return fem.Function(fem.DG0Space(self.amesh), self.part.restrict_cell(vals), dtype=np.float64)
-        return fem.Function(fem.functionspace(self.amesh, ("Lagrange", 1)), self.part.restrict_nodal(vals[:self.mesh.n_nodes]),
-                            dtype=np.float64)
+            return fem.Function.from_device(fem.DG0Space(self.amesh), self.part.restrict_cell(vals))
+        return fem.Function.from_device(fem.functionspace(self.amesh, ("Lagrange", 1)),
+                                        self.part.restrict_nodal(vals[:self.mesh.n_nodes]))
 
     def _set(self, lefts, rights, problem_type):
         be, n = self.V.be, self.local_size

@@ -333,6 +333,8 @@ class ShiftedSolver:
                 else:
                     mg.set_shift(t.get("A", 0), t.get("B", 0), t.get("C", 0), fine_values=fine_vals)
                 Pop = mg.fine_operator() if (len(mg.levels) > 1 and ops.part is None) else P
+                if ops.part is not None and hasattr(ops.space, "matrix_sell"):
+                    Pop = ops.space.matrix_sell(P_values) or P
                 if hier is not None:
                     hier.set_fine(P_values)
                 elif ops.part is not None:
