@@ -52,6 +52,7 @@ SIGNATURES = {
     "hx_scale_copy": [i64, vp, vp, vp, vp, vp],
     "hx_axpby": [i64, vp, vp, vp, vp, vp],
     "hx_basis_rotate": [i64, i32, i32, vp, i64, vp, i32, vp, i64, vp],
+    "hx_basis_rotate_dmma": [i64, i32, i32, vp, i64, vp, i32, vp, i64, vp],
     "hx_jacobi_sweep": [i32, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp],
     "hx_extract_diag_inv": [i32, vp, vp, vp, vp, vp],
     "hx_ilu0_factor": [i32, vp, vp, vp, vp, i32, vp, vp, vp],

@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from .backend import CsrMatrix
+from .phases import phase
 
 c128 = torch.complex128
 f64 = torch.float64
@@ -216,7 +217,8 @@ class AMG:
             if getattr(be, "supports_spgemm", False) and n >= self.native_min_rows:
                 from .spgemm import Overflow
                 try:
-                    L.P, L.R, pat, a_re, c_re, b_cx = self._coarsen_native(be, pat, a_re, c_re, b_cx, agg, nc, tval, tau)
+                    with phase("amg_setup_native_spgemm"):
+                        L.P, L.R, pat, a_re, c_re, b_cx = self._coarsen_native(be, pat, a_re, c_re, b_cx, agg, nc, tval, tau)
                     csum = torch.zeros(nc, 3, dtype=f64, device=dev)
                     csum.index_add_(0, agg, coords)
                     coords = csum / cnt.view(-1, 1)

@@ -194,12 +194,16 @@ class CudaBackend:
         _lib.call("hx_axpby", y.numel(), _c2(a), x.data_ptr(), _c2(b) if b is not None else None, y.data_ptr(), self.stream)
         return y
 
-    def basis_rotate(self, V, m, Q, kout, Vout):
+    #: restart rotation on the FP64 tensor cores (DMMA) or the FP64 CUDA cores; timed by tools/rotate_bench.py
+    ROTATE_TENSOR_CORES = True
+
+    def basis_rotate(self, V, m, Q, kout, Vout, tensor_cores=None):
         """Vout[c] = sum_j Q[c, j] V[j]  (Q: (kout, m) row-major tensor = column-major m x kout)."""
         assert Q.is_contiguous() and Q.shape[1] >= m
         n = V.shape[1]
-        _lib.call("hx_basis_rotate", n, m, kout, V.data_ptr(), V.stride(0), Q.data_ptr(), Q.stride(0), Vout.data_ptr(),
-                  Vout.stride(0), self.stream)
+        tc = self.ROTATE_TENSOR_CORES if tensor_cores is None else tensor_cores
+        _lib.call("hx_basis_rotate_dmma" if tc else "hx_basis_rotate", n, m, kout, V.data_ptr(), V.stride(0), Q.data_ptr(),
+                  Q.stride(0), Vout.data_ptr(), Vout.stride(0), self.stream)
         return Vout
 
     # ---- preconditioner pieces -----------------------------------------------------------

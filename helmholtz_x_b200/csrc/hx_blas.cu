@@ -172,6 +172,73 @@ basis_rotate_kernel(long long n, int m, int kout, const double2* __restrict__ V,
     }
 }
 
+// ---- the same contraction on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64) --------------------
+// Vout (kout x n) = Q^T (kout x m) * V (m x n), complex, as four real m8n8k4 products per k-step:
+// Cr += Qr*Vr + (-Qi)*Vi, Ci += Qr*Vi + Qi*Vr.  A warp owns 16 output vectors (two m8 tiles) and walks
+// the vector index in chunks of 8; the V fragment of a k-step is four rows x 8 consecutive complex
+// entries (4 x 128 B per load instruction).  Q^T lives in shared memory (split re / -im / im).
+// Per loaded V entry: 16 complex FMAs on the tensor pipe instead of 8 on the FP64 CUDA cores, and half
+// the re-reads of V for kout > 8.
+constexpr int kMmaWarps = 8;
+constexpr int kMmaTileM = 16;
+
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kMmaWarps * 32)
+basis_rotate_dmma_kernel(long long n, int m, int kout, const double2* __restrict__ V, long long ld,
+                         const double2* __restrict__ Q, int ldq, double2* __restrict__ Vout, long long ldout) {
+    extern __shared__ double qsm[];               // [3][kMmaTileM][m4]: re, -im, im of Q^T (zero padded)
+    const int m4 = (m + 3) & ~3;
+    const int c0 = blockIdx.y * kMmaTileM;
+    double* qr = qsm;
+    double* qni = qsm + kMmaTileM * m4;
+    double* qi = qsm + 2 * kMmaTileM * m4;
+    for (int e = threadIdx.x; e < kMmaTileM * m4; e += blockDim.x) {
+        const int c = e / m4, j = e % m4;
+        double2 q = make_double2(0.0, 0.0);
+        if (c0 + c < kout && j < m) q = Q[j + (long long)(c0 + c) * ldq];
+        qr[e] = q.x; qni[e] = -q.y; qi[e] = q.y;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ar = lane >> 2, ak = lane & 3;      // A fragment: row (output vector), k
+    const long long tiles = (n + 7) / 8;
+    for (long long t = (long long)blockIdx.x * kMmaWarps + warp; t < tiles; t += (long long)gridDim.x * kMmaWarps) {
+        const long long i0 = t * 8;
+        const long long ib = i0 + (lane >> 2);    // B fragment: column (vector entry) of this lane
+        const bool inb = ib < n;
+        double cr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ci[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int j0 = 0; j0 < m4; j0 += 4) {
+            const int j = j0 + ak;
+            double2 v = make_double2(0.0, 0.0);
+            if (inb && j < m) v = ld_stream(V + (long long)j * ld + ib);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int qe = (h * 8 + ar) * m4 + j;
+                const double a_r = qr[qe], a_ni = qni[qe], a_i = qi[qe];
+                dmma_8x8x4(cr[h][0], cr[h][1], a_r, v.x);
+                dmma_8x8x4(cr[h][0], cr[h][1], a_ni, v.y);
+                dmma_8x8x4(ci[h][0], ci[h][1], a_r, v.y);
+                dmma_8x8x4(ci[h][0], ci[h][1], a_i, v.x);
+            }
+        }
+        // C fragment: row = lane>>2 (output vector), columns 2*(lane&3) + {0,1}
+        const long long ic = i0 + 2 * (lane & 3);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = c0 + h * 8 + (lane >> 2);
+            if (c < kout) {
+                double2* o = Vout + (long long)c * ldout + ic;
+                if (ic < n) o[0] = make_double2(cr[h][0], ci[h][0]);
+                if (ic + 1 < n) o[1] = make_double2(cr[h][1], ci[h][1]);
+            }
+        }
+    }
+}
+
 // ---- dense coarse solve: in-place Gauss-Jordan inverse, partial pivoting, one CTA -----
 constexpr int kGJThreads = 1024;
 __global__ void __launch_bounds__(kGJThreads)
@@ -347,6 +414,23 @@ extern "C" int hx_basis_rotate(int64_t n, int m, int kout, const double* V, int6
     basis_rotate_kernel<<<grid, kRedThreads, (size_t)m * kRotTile * sizeof(double2), (cudaStream_t)stream>>>(
         n, m, kout, (const double2*)V, ld, (const double2*)Q, ldq, (double2*)Vout, ldout);
     return check_launch("basis_rotate_kernel");
+}
+
+extern "C" int hx_basis_rotate_dmma(int64_t n, int m, int kout, const double* V, int64_t ld, const double* Q, int ldq,
+                                    double* Vout, int64_t ldout, hx_stream_t stream) {
+    if (n <= 0 || kout <= 0) return HX_OK;
+    if (m > 512) return fail(HX_ERR_CAPACITY, "hx_basis_rotate_dmma: m > 512%s%s");
+    const int m4 = (m + 3) & ~3;
+    const size_t smem = (size_t)3 * kMmaTileM * m4 * sizeof(double);
+    if (smem > 48 * 1024)
+        HX_CUDA(cudaFuncSetAttribute(basis_rotate_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long tiles = (n + 7) / 8;
+    long long gx = ceil_div<long long>(tiles, kMmaWarps);
+    if (gx > kNumSMs * 8) gx = kNumSMs * 8;
+    dim3 grid((unsigned)gx, ceil_div(kout, kMmaTileM));
+    basis_rotate_dmma_kernel<<<grid, kMmaWarps * 32, smem, (cudaStream_t)stream>>>(
+        n, m, kout, (const double2*)V, ld, (const double2*)Q, ldq, (double2*)Vout, ldout);
+    return check_launch("basis_rotate_dmma_kernel");
 }
 
 extern "C" int hx_dense_inverse(int n, double* a, int32_t* info_dev, hx_stream_t stream) {

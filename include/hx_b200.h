@@ -149,6 +149,11 @@ int hx_axpby(int64_t n, const double* a_h, const double* x_c128, const double* b
 int hx_basis_rotate(int64_t n, int m, int kout, const double* V_c128, int64_t ld, const double* Q_c128,
                     int ldq, double* Vout_c128, int64_t ldout, hx_stream_t stream);
 
+/* the same contraction on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64; four real products per
+ * complex k-step, 16 output vectors per pass over V) -- SLEPc BVMultInPlace at the Krylov-Schur restart */
+int hx_basis_rotate_dmma(int64_t n, int m, int kout, const double* V_c128, int64_t ld, const double* Q_c128,
+                         int ldq, double* Vout_c128, int64_t ldout, hx_stream_t stream);
+
 /* ------------------------------------------------------------------ K9
  * inner solve building blocks (what PETSc KSP+PC LU/MUMPS did behind ST sinvert) */
 /* xout = xin + omega * dinv .* (b - M xin); xin NULL => xout = omega*dinv.*b */

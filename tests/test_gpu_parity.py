@@ -313,6 +313,28 @@ def test_basis_kernels_match_numpy_and_are_deterministic():
     assert relmax(Vout.cpu().numpy(), Q @ Vh) < 1e-13
 
 
+@pytest.mark.parametrize("n,m,kout", [(100003, 19, 11), (4099, 64, 33), (7, 3, 1), (50000, 20, 4)])
+def test_basis_rotate_on_fp64_tensor_cores_matches_the_fma_kernel(n, m, kout):
+    """hx_basis_rotate_dmma (mma.sync.m8n8k4.f64, the restart rotation V <- V Q of Krylov-Schur; SLEPc
+    BVMultInPlace behind helmholtz_x/eigensolvers.py:62,113) against NumPy and the CUDA-core kernel."""
+    b = be()
+    rng = np.random.default_rng(n + m)
+    Vh = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    Q = rng.standard_normal((kout, m)) + 1j * rng.standard_normal((kout, m))
+    V = b.asarray(Vh, dtype=torch.complex128)
+    Qd = b.asarray(Q, dtype=torch.complex128)
+    ref = Q @ Vh
+    out_t = torch.full((kout, n), float("nan"), dtype=torch.complex128, device=b.device)
+    b.basis_rotate(V, m, Qd, kout, out_t, tensor_cores=True)
+    assert relmax(out_t.cpu().numpy(), ref) < 1e-13
+    out_f = b.zeros(kout, n)
+    b.basis_rotate(V, m, Qd, kout, out_f, tensor_cores=False)
+    assert relmax(out_t.cpu().numpy(), out_f.cpu().numpy()) < 1e-13
+    again = b.zeros(kout, n)
+    b.basis_rotate(V, m, Qd, kout, again, tensor_cores=True)
+    assert torch.equal(again, out_t)
+
+
 def test_dense_inverse_and_gemv():
     b = be()
     rng = np.random.default_rng(11)
