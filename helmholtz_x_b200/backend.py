@@ -194,14 +194,19 @@ class CudaBackend:
         _lib.call("hx_axpby", y.numel(), _c2(a), x.data_ptr(), _c2(b) if b is not None else None, y.data_ptr(), self.stream)
         return y
 
-    #: restart rotation on the FP64 tensor cores (DMMA) or the FP64 CUDA cores; timed by tools/rotate_bench.py
-    ROTATE_TENSOR_CORES = True
+    #: restart rotation on the FP64 tensor cores (DMMA, 16 output vectors per pass over V) when more than 8
+    #: vectors come out, on the FP64 CUDA cores (8 per pass) otherwise.  Measured on B200
+    #: (profiles/r2_rotate_bench_dmma_vs_fma.json, n = 10 M): m=19,k=10 1.09 ms vs 1.69 ms (4.24 vs 2.74 TB/s),
+    #: m=24,k=12 1.42 vs 2.08 ms, m=64,k=32 9.46 vs 10.77 ms; m=64,k=8 4.61 vs 3.11 ms (half of the tile is padding).
+    ROTATE_TENSOR_CORES = None
 
     def basis_rotate(self, V, m, Q, kout, Vout, tensor_cores=None):
         """Vout[c] = sum_j Q[c, j] V[j]  (Q: (kout, m) row-major tensor = column-major m x kout)."""
         assert Q.is_contiguous() and Q.shape[1] >= m
         n = V.shape[1]
-        tc = self.ROTATE_TENSOR_CORES if tensor_cores is None else tensor_cores
+        tc = tensor_cores if tensor_cores is not None else self.ROTATE_TENSOR_CORES
+        if tc is None:
+            tc = kout > 8
         _lib.call("hx_basis_rotate_dmma" if tc else "hx_basis_rotate", n, m, kout, V.data_ptr(), V.stride(0), Q.data_ptr(),
                   Q.stride(0), Vout.data_ptr(), Vout.stride(0), self.stream)
         return Vout
