@@ -216,6 +216,9 @@ def iteration_breakdown(be, ops, peak):
 
     t_cycle = timed(lambda: mg.apply(b, y), 50)
     t_apply = timed(lambda: be.spmv(st["Pop"], b, y), 50)
+    # one visit of level l and everything below it (the part of the cycle that runs replicated on several GPUs)
+    from_level = {f"from_level{l}": round(timed(lambda l=l: mg._cycle(l, mg.levels[l].b_), 30), 1)
+                  for l in range(1, len(mg.levels))}
     basis = st["basis"]
     k = min(32, basis.m - 1)
     for j in range(k + 1):
@@ -241,7 +244,9 @@ def iteration_breakdown(be, ops, peak):
             "gram_schmidt_kernels": "multi_dot_kernel, multi_axpy_kernel (x passes), scale_copy_kernel",
             "gram_schmidt_bytes": nbytes, "gram_schmidt_gbs": round(gbs, 1),
             "gram_schmidt_frac_of_peak": round(gbs / peak, 4),
-            "amg_levels": mg.sizes, "k": k}
+            "amg_levels": mg.sizes, "amg_level_nnz": [L.pattern.nnz for L in mg.levels], "cycle_visit_us": from_level,
+            "cycle_shape": {"w_from": mg.w_from, "w_to": (mg.w_to if mg.w_to < 10 ** 6 else None), "nu": [L.nu for L in mg.levels]},
+            "k": k}
 
 
 def _omega_reference(dofs):

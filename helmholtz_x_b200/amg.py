@@ -128,11 +128,35 @@ class Level:
     pass
 
 
+def filter_prolongator(P: CsrMatrix, theta):
+    """Drop the entries of a smoothed prolongator below theta * (largest entry of the row) and rescale the
+    kept ones so that every row keeps its sum (constants stay in the range of P).  The Galerkin operators
+    R A P inherit the square of the saving: without it the level operators of the 10 M-DoF annulus carry
+    14.8 / 70 / 473 / 1464 nonzeros per row and the coarse levels cost as much as the fine one."""
+    if not theta:
+        return P
+    n, dev = P.n_rows, P.values.device
+    rows = _rows_of(P.indptr, P.nnz)
+    a = P.values.abs()
+    rmax = torch.zeros(n, dtype=a.dtype, device=dev).scatter_reduce_(0, rows, a, reduce="amax", include_self=True)
+    keep = a >= theta * rmax[rows]
+    rsum = torch.zeros(n, dtype=P.values.dtype, device=dev).index_add_(0, rows, P.values)
+    ksum = torch.zeros(n, dtype=P.values.dtype, device=dev).index_add_(0, rows[keep], P.values[keep])
+    scale = torch.where(ksum.abs() > 1e-300, rsum / ksum, torch.ones_like(ksum))
+    kr = rows[keep]
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(torch.bincount(kr, minlength=n), 0)
+    return CsrMatrix(n, P.n_cols, indptr.to(torch.int32).contiguous(), P.indices[keep].contiguous(),
+                     (P.values[keep] * scale[kr]).contiguous())
+
+
 #: how the spectral radius of D^-1 K is estimated for the prolongator smoothing:
 #: "smoothpower" (default) = 12 power iterations from a smooth start vector: underestimates rho (1.45-1.6 vs ~2),
 #: i.e. over-relaxes the prolongator smoothing, which measured BEST (25 vs 30 GMRES iterations at 60k DoF,
 #: 36 vs 45 at 250k); "gershgorin" = max_i sum_j |k_ij| / k_ii (safe upper bound); "power" = random start
 RHO_MODE = "smoothpower"
+#: prolongator filter threshold (filter_prolongator); HX_AMG_PFILTER overrides
+P_FILTER = 0.0
 #: fine-level rows from which the W-cycle pays on B200 (see AMG.__init__)
 W_AUTO_MIN_ROWS = 3_000_000
 
@@ -140,7 +164,7 @@ W_AUTO_MIN_ROWS = 3_000_000
 class AMG:
     def __init__(self, be, A: CsrMatrix, C: CsrMatrix, B: CsrMatrix | None, coords, tau=None, agg_size=16,
                  coarse_max=900, max_levels=12, nu=2, omega=2.0 / 3.0, sell_min_rows=250000, precision="single",
-                 w_from=None, smoother=None, w_to=None):
+                 w_from=None, smoother=None, w_to=None, p_filter=None, nu_coarse=None, agg_coarse=None):
         """A, C real-valued, B complex or None -- all on ONE shared fine pattern.
         precision="single": the V-cycle (smoother, residual, transfers) runs in complex64 --
         it is only a preconditioner; GMRES and everything outside stay complex128."""
@@ -179,6 +203,12 @@ class AMG:
         self.w_from = w_from
         self.w_to = w_to if w_to is not None else 10 ** 6
         self.native_min_rows = 20000
+        # sweeps per smoothing on levels >= 2 and aggregate size from level 1 down (the coarse operators of
+        # smoothed aggregation are dense -- 70 / 470 nonzeros per row on levels 1 / 2 -- so what is spent there
+        # is tuned separately from the fine level)
+        self.nu_coarse = int(os.environ.get("HX_AMG_NU_COARSE", nu)) if nu_coarse is None else int(nu_coarse)
+        self.agg_coarse = int(os.environ.get("HX_AMG_AGG_COARSE", agg_size)) if agg_coarse is None else int(agg_coarse)
+        self.p_filter = float(os.environ.get("HX_AMG_PFILTER", P_FILTER)) if p_filter is None else float(p_filter)
         # the V-cycle is a fixed sequence of ~25 small launches on fixed buffers: captured once per
         # shift in a CUDA graph and replayed (HX_AMG_GRAPH=0 launches it kernel by kernel)
         self.use_graph = getattr(be, "supports_graphs", False) and os.environ.get("HX_AMG_GRAPH", "1") != "0"
@@ -209,7 +239,7 @@ class AMG:
             n = L.n
             order = morton_order(coords)
             agg = torch.empty(n, dtype=torch.int64, device=dev)
-            agg[order] = torch.arange(n, device=dev) // agg_size
+            agg[order] = torch.arange(n, device=dev) // (agg_size if len(self.levels) == 1 else self.agg_coarse)
             nc = int(agg.max().item()) + 1
             L.agg = agg                           # dof -> aggregate (ownership of the coarse dofs on several GPUs)
             cnt = torch.bincount(agg, minlength=nc).to(f64)
@@ -257,6 +287,9 @@ class AMG:
             ST = _spmm(S, T)
             Pm = (T - (4.0 / (3.0 * rho)) * ST).coalesce()
             del K, S, ST, T, v
+            if self.p_filter:
+                Pf = filter_prolongator(_from_coo(Pm), self.p_filter)
+                Pm = _to_coo(Pf)
             Rm = Pm.t().coalesce()
 
             def galerkin(vals):
@@ -300,7 +333,8 @@ class AMG:
             coords = csum / cnt.view(-1, 1)
         # work vectors
         wd = self.wdtype
-        for L in self.levels:
+        for li, L in enumerate(self.levels):
+            L.nu = self.nu if li < 2 else self.nu_coarse
             L.x = be.zeros(L.n, dtype=wd); L.b_ = be.zeros(L.n, dtype=wd)
             L.r = be.zeros(L.n, dtype=wd); L.t = be.zeros(L.n, dtype=wd)
             if self.w_from is not None:
@@ -343,7 +377,7 @@ class AMG:
         keys = _rows_of(ST.indptr, ST.nnz) * nc + ST.indices.long()                 # sorted (CSR order)
         pos = torch.searchsorted(keys, torch.arange(n, device=dev) * nc + agg)
         pvals[pos] += tval                                                          # + T (its entry lies in the pattern of S*T)
-        P = ST.with_values(pvals.contiguous())
+        P = filter_prolongator(ST.with_values(pvals.contiguous()), self.p_filter)
         R = spgemm.transpose(P)
         yp = spgemm.symbolic(be, pat, P)
         Ypat = CsrMatrix(n, nc, yp[0], yp[1], None)
@@ -387,7 +421,7 @@ class AMG:
             if i < len(self.levels) - 1:
                 be.diag_inv(L.M, L.dinv)
                 L.dinv_w = L.dinv.to(self.wdtype) if self.single else L.dinv
-                L.omegas = self._chebyshev_dampings(L) if self.smoother == "chebyshev" else self.omegas
+                L.omegas = self._chebyshev_dampings(L) if self.smoother == "chebyshev" else (self.omegas * 2)[:L.nu]
                 if self.sell_min_rows is not None and L.n >= self.sell_min_rows:
                     from .sell import SellMatrix, SellPattern
                     if L.sellp is None:
@@ -434,7 +468,7 @@ class AMG:
         rho *= safety
         a, b = rho / alpha, rho
         mid, half = 0.5 * (a + b), 0.5 * (b - a)
-        roots = [mid + half * np.cos(np.pi * (2 * k + 1) / (2 * self.nu)) for k in range(self.nu)]
+        roots = [mid + half * np.cos(np.pi * (2 * k + 1) / (2 * L.nu)) for k in range(L.nu)]
         L.rho = rho
         return [float(1.0 / r) for r in sorted(roots, reverse=True)]
 
@@ -447,7 +481,7 @@ class AMG:
         if first_zero:
             be.jacobi_sweep(L.Mop, L.dinv_w, b, None, cur, om[0])
             k = 1
-        for s in range(k, self.nu):
+        for s in range(k, L.nu):
             be.jacobi_sweep(L.Mop, L.dinv_w, b, cur, other, om[s])
             cur, other = other, cur
         if cur is not L.x:

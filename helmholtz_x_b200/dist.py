@@ -672,7 +672,7 @@ class DistHierarchy:
         if first_zero:
             be.jacobi_sweep(D.M, D.dinv_w, D.b, None, D.xa, D.omegas[0])
             k = 1
-        for s in range(k, self.nu):
+        for s in range(k, len(D.omegas)):
             D.halo.exchange(D.xa)
             be.jacobi_sweep(D.M, D.dinv_w, D.b, D.xa, D.xb, D.omegas[s])
             D.xa, D.xb = D.xb, D.xa
