@@ -3,9 +3,9 @@
 the reference's config-1 (Rijke3D EPS FPI) and config-3 (full annulus PEP FPI, 16 pointwise flames) through
 the public API on N ranks, compared with the golden logs.
 
-Default: one rank per GPU, NCCL for the set-up plumbing.  --same-device: every rank uses cuda:0 and gloo
-carries the plumbing -- the peer-memory kernels (CUDA IPC works between processes on one device) and the
-whole distributed host logic then run on a ONE-GPU box, which is what tests/test_gpu_dist.py does."""
+One rank per GPU, NCCL for the set-up plumbing.  (Ranks must NOT share a GPU: the peer-memory kernels
+of different ranks wait on one another, and nothing guarantees that two processes' kernels run at the same
+time on one device -- B200_PROFILING.md reports Xid 109 for exactly that.)"""
 import argparse
 import contextlib
 import io
@@ -85,17 +85,14 @@ def unit_checks(rank, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--same-device", action="store_true")
     ap.add_argument("--cases", default="rijke3d,annulus")
     ap.add_argument("--no-unit", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    if args.same_device:
-        torch.cuda.set_device(0)
-        dist.init_process_group("gloo")
-    else:
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if torch.cuda.device_count() < world:
+        raise SystemExit("dist_check.py needs one GPU per rank")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     import __graft_entry__ as ge
     if rank == 0:
         ge.build()
@@ -106,7 +103,7 @@ def main():
     from helmholtz_x_b200.eigensolvers import fixed_point_iteration
     from helmholtz_x_b200.eigenvectors import normalize_eigenvector
     G = cases.golden_values()
-    out = {"world": world, "transport": peer.transport(), "same_device": args.same_device}
+    out = {"world": world, "transport": peer.transport()}
     if not args.no_unit and peer.transport() == "peer":
         out["unit"] = unit_checks(rank, world)
     table = {"rijke3d": (cases.rijke3d, "rijke3d_active_fpi"), "annulus": (cases.annulus, "annulus_fpi_direct")}
