@@ -155,8 +155,13 @@ def filter_prolongator(P: CsrMatrix, theta):
 #: i.e. over-relaxes the prolongator smoothing, which measured BEST (25 vs 30 GMRES iterations at 60k DoF,
 #: 36 vs 45 at 250k); "gershgorin" = max_i sum_j |k_ij| / k_ii (safe upper bound); "power" = random start
 RHO_MODE = "smoothpower"
-#: prolongator filter threshold (filter_prolongator); HX_AMG_PFILTER overrides
-P_FILTER = 0.0
+#: prolongator filter threshold (filter_prolongator) and aggregate size from level 1 down; HX_AMG_PFILTER /
+#: HX_AMG_AGG_COARSE override.  Timed on B200 (profiles/r2_hier_*.json, 5 M DoF, inner-solve seconds of one step):
+#: 16 / no filter 13.67; 32 / no filter 12.29; 16 / 0.1 12.93; 32 / 0.1 11.81 (with the W-cycle from level 1: 10.85);
+#: 32 / 0.15 11.97; 32 / 0.2 12.22; 24 / 0.1 12.61; 48 / 0.1 13.23; 64 / no filter 13.17.  Level nonzeros
+#: 73.8 M / 21.4 M / 8.5 M / 1.1 M become 73.8 M / 17.9 M / 1.8 M / 37 k: one visit of level 2 and below 185 -> 84 us.
+P_FILTER = 0.1
+AGG_COARSE = 32
 #: fine-level rows from which the W-cycle pays on B200 (see AMG.__init__)
 W_AUTO_MIN_ROWS = 3_000_000
 
@@ -207,7 +212,7 @@ class AMG:
         # smoothed aggregation are dense -- 70 / 470 nonzeros per row on levels 1 / 2 -- so what is spent there
         # is tuned separately from the fine level)
         self.nu_coarse = int(os.environ.get("HX_AMG_NU_COARSE", nu)) if nu_coarse is None else int(nu_coarse)
-        self.agg_coarse = int(os.environ.get("HX_AMG_AGG_COARSE", agg_size)) if agg_coarse is None else int(agg_coarse)
+        self.agg_coarse = int(os.environ.get("HX_AMG_AGG_COARSE", max(AGG_COARSE, agg_size))) if agg_coarse is None else int(agg_coarse)
         self.p_filter = float(os.environ.get("HX_AMG_PFILTER", P_FILTER)) if p_filter is None else float(p_filter)
         # the V-cycle is a fixed sequence of ~25 small launches on fixed buffers: captured once per
         # shift in a CUDA graph and replayed (HX_AMG_GRAPH=0 launches it kernel by kernel)
@@ -393,7 +398,27 @@ class AMG:
         c_c = galerkin_any(c_re)
         b_c = None
         if b_cx is not None:
-            b_c = torch.complex(galerkin(b_cx.real), galerkin(b_cx.imag))
+            nzb = torch.nonzero(b_cx).reshape(-1)
+            if nzb.numel() * 8 < b_cx.numel():
+                # B lives on the impedance boundary only: its Galerkin product runs on the compacted entries
+                # (own small symbolic pattern), scattered afterwards into the pattern shared with A and C
+                brow = rows[nzb]
+                bptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+                bptr[1:] = torch.cumsum(torch.bincount(brow, minlength=n), 0)
+                Bc = CsrMatrix(n, n, bptr.to(torch.int32).contiguous(), pat.indices[nzb].contiguous(), None)
+                ypb = spgemm.symbolic(be, Bc, P)
+                zpb = spgemm.symbolic(be, R, CsrMatrix(n, nc, ypb[0], ypb[1], None))
+                parts = []
+                for comp in (b_cx.real[nzb].contiguous(), b_cx.imag[nzb].contiguous()):
+                    yv = spgemm.numeric(be, Bc.with_values(comp), P, ypb[0], ypb[1])
+                    parts.append(spgemm.numeric(be, R, CsrMatrix(n, nc, ypb[0], ypb[1], yv), zpb[0], zpb[1]))
+                nzc = int(zpb[1].numel())
+                kb = _rows_of(zpb[0], nzc) * nc + zpb[1].long()
+                kall = _rows_of(zp[0], int(zp[1].numel())) * nc + zp[1].long()
+                b_c = torch.zeros(int(zp[1].numel()), dtype=c128, device=dev)
+                b_c[torch.searchsorted(kall, kb)] = torch.complex(parts[0][:nzc], parts[1][:nzc])
+            else:
+                b_c = torch.complex(galerkin(b_cx.real), galerkin(b_cx.imag))
         pat_c = CsrMatrix(nc, nc, zp[0], zp[1], torch.zeros(int(zp[1].numel()), dtype=f64, device=dev))
         return P, R, pat_c, a_c, c_c, b_c
 

@@ -116,7 +116,9 @@ def _synthetic_worker(rank, world, port, q, hierarchy=False):
             per_solve = ops.stats["inner_iterations"] / ops.stats["inner_solves"]
             per_solve1 = single / ops1.stats["inner_solves"]
             assert abs(per_solve - per_solve1) <= 0.05 * per_solve1 + 0.5, (ops.stats, ops1.stats)
-            assert abs(ops.stats["inner_solves"] - ops1.stats["inner_solves"]) <= 3
+            # the start vectors differ (each rank seeds its own slice), so one run may need a Krylov-Schur
+            # restart the other does not: at most one basis (ncv = 19) of extra solves
+            assert abs(ops.stats["inner_solves"] - ops1.stats["inner_solves"]) <= 20, (ops.stats, ops1.stats)
         q.put((rank, "ok", (ops.stats["inner_iterations"], single)))
     except Exception:      # noqa: BLE001
         import traceback

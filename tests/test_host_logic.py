@@ -193,6 +193,25 @@ def test_native_spgemm_coarsening_path_matches_library_path(rijke, monkeypatch):
     c1n = to_sp(nat.levels[1].pattern, nat.levels[1].c)
     c1r = to_sp(ref.levels[1].pattern, ref.levels[1].c)
     assert abs(c1n - c1r).max() < 1e-9 * abs(c1r).max()
+    # impedance matrix B (nonzero on the Robin boundary only: compacted Galerkin product) and the prolongator filter
+    hp = HostOperators(cases.prf_rijke3d())
+    bp = hp.ops.be
+    A, C, B = (hp.V.matrix(hp.ops.base[k]) for k in ("A", "C", "B"))
+    assert int(torch.count_nonzero(B.values)) * 8 < B.values.numel()
+    ref = amg.AMG(bp, A, C, B, hp.V.dof_coords, agg_size=8, p_filter=0.1)
+    bp.supports_spgemm = True
+    nat = NativeAMG(bp, A, C, B, hp.V.dof_coords, agg_size=8, p_filter=0.1)
+    bp.supports_spgemm = False
+    assert nat.sizes == ref.sizes
+    assert nat.levels[0].P.nnz == ref.levels[0].P.nnz < amg.AMG(bp, A, C, B, hp.V.dof_coords, agg_size=8, p_filter=0.0).levels[0].P.nnz
+    for name in ("a", "c", "b"):
+        mn = to_sp(nat.levels[1].pattern, getattr(nat.levels[1], name))
+        mr = to_sp(ref.levels[1].pattern, getattr(ref.levels[1], name))
+        assert abs(mn - mr).max() < 1e-9 * abs(mr).max(), name
+    ones = torch.ones(ref.levels[1].n, dtype=torch.float64)
+    rowsum = to_sp(ref.levels[0].P) @ ones.numpy()
+    unf = to_sp(amg.AMG(bp, A, C, B, hp.V.dof_coords, agg_size=8, p_filter=0.0).levels[0].P) @ ones.numpy()
+    assert np.allclose(rowsum, unf, rtol=1e-12, atol=1e-14)            # the filter keeps every row sum
 
 
 def test_bloch_reduction_host_logic():
