@@ -39,6 +39,8 @@ SIGNATURES = {
     "hx_spmv_cc": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "hx_spmv_sc": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "hx_spmv_sell_cc": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "hx_spmv_sell_sc": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "hx_sell_gather_s": [i64, vp, vp, vp, vp],
     "hx_jacobi_sell_c": [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp],
     "hx_jacobi_sweep_c": [i32, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp],
     "hx_sell_gather_c": [i64, vp, vp, vp, vp],

@@ -162,8 +162,10 @@ RHO_MODE = "smoothpower"
 #: 73.8 M / 21.4 M / 8.5 M / 1.1 M become 73.8 M / 17.9 M / 1.8 M / 37 k: one visit of level 2 and below 185 -> 84 us.
 P_FILTER = 0.1
 AGG_COARSE = 32
-#: fine-level rows from which the W-cycle pays on B200 (see AMG.__init__)
-W_AUTO_MIN_ROWS = 3_000_000
+#: fine-level rows from which the W-cycle pays on B200 (see AMG.__init__).  With the coarse levels above
+#: (profiles/r2_shape2_*.json, whole step): 250 k DoF V 1.00 s / W from level 1 1.12 s; 1 M 3.22 / 2.98 s
+#: (level 2 alone twice: 2.94 s); 10 M: W from level 1 27.1 s, level 2 alone twice 31.0 s.
+W_AUTO_MIN_ROWS = 600_000
 
 
 class AMG:
@@ -176,10 +178,8 @@ class AMG:
         self.be, self.nu, self.omega = be, nu, omega
         # W-cycle: levels >= w_from are visited twice per visit of their parent (None: V-cycle).  The
         # V-cycle count grows with the number of levels, the W-cycle count hardly does; the extra coarse
-        # visits are latency-bound.  Measured on B200 (profiles/r2_ab_switches.md, synthetic annulus, whole
-        # step): 1 M DoF V 3.53 s / W from level 1 4.01 s; 10 M DoF V 50.5 s / W 43.8 s (inner iterations
-        # 7108 -> 4388).  Default (HX_AMG_WCYCLE unset or "auto"): W from level 1 on meshes of at least
-        # W_AUTO_MIN_ROWS rows, V below; HX_AMG_WCYCLE=<level> forces it, "off" forces the V-cycle.
+        # visits are latency-bound.  Default (HX_AMG_WCYCLE unset or "auto"): W from level 1 on meshes of at
+        # least W_AUTO_MIN_ROWS rows, V below; HX_AMG_WCYCLE=<from>[:<to>] forces a shape, "off" the V-cycle.
         # damping of sweep s (pre- and post-smoothing alike); a list makes the nu sweeps a polynomial
         # smoother with those roots (e.g. the Chebyshev pair) at no extra cost
         self.omegas = list(omega) if isinstance(omega, (list, tuple)) else [omega] * nu
@@ -196,9 +196,7 @@ class AMG:
         if w_from is None:
             env = os.environ.get("HX_AMG_WCYCLE", "auto")
             if env == "auto":
-                # level 2 alone visited twice: cheapest cycle of the shapes timed at 10 M DoF (whole step:
-                # W from level 1 35.4 s, levels 1-2 34.4 s, level 1 37.4 s, level 2 33.7 s; V 50.5 s)
-                w_from, w_to = (2, 2) if A.n_rows >= W_AUTO_MIN_ROWS else (None, w_to)
+                w_from = 1 if A.n_rows >= W_AUTO_MIN_ROWS else None
             elif env not in ("off", ""):
                 # "<from>" or "<from>:<to>": levels from..to (inclusive) are visited twice per visit of their parent
                 lo, _, hi = env.partition(":")
@@ -352,10 +350,23 @@ class AMG:
             if self.single and hasattr(L, "P"):
                 L.P = L.P.with_values(L.P.values.float())
                 L.R = L.R.with_values(L.R.values.float())
+            if hasattr(L, "P"):
+                # transfer operators of the cycle: SELL-32 (one thread per row, coalesced) where the CSR-vector kernel
+                # is latency-bound on the short rows -- prolongation 336 -> us at 10 M DoF (5.6 nonzeros per row)
+                L.P_op, L.R_op = self._transfer_op(L.P), self._transfer_op(L.R)
         last = self.levels[-1]
         last.b64 = be.zeros(last.n)
         last.x64 = be.zeros(last.n)
         self.coarse_inv = None
+
+    def _transfer_op(self, M):
+        """SELL-32 copy of a float32 transfer operator on large levels (the CSR matrix otherwise)."""
+        if (self.sell_min_rows is None or M.n_rows < self.sell_min_rows or M.values.dtype != torch.float32
+                or os.environ.get("HX_AMG_SELL_TRANSFER", "1") == "0"):
+            return M
+        from .sell import SellMatrix, SellPattern
+        p = SellPattern(self.be, M.indptr, M.indices, M.n_rows, M.n_cols)
+        return SellMatrix(p, p.values_from_csr(M.values))
 
     def _coarsen_native(self, be, pat, a_re, c_re, b_cx, agg, nc, tval, tau):
         """One coarsening step with the library's own SpGEMM kernels (hx_spgemm_*): P = (I - w D^-1 K) T,
@@ -527,7 +538,7 @@ class AMG:
         self._smooth(L, b, L.x, first_zero=True)
         be.spmv(L.Mop, L.x, L.r, alpha=-1.0, beta=1.0, y0=b)         # r = b - M x
         Lc = self.levels[i + 1]
-        be.spmv(L.R, L.r, Lc.b_)
+        be.spmv(L.R_op, L.r, Lc.b_)
         xc = self._cycle(i + 1, Lc.b_)
         if self.w_from is not None and self.w_from <= i + 1 <= self.w_to and i + 1 < len(self.levels) - 1:
             # second visit: the cycle applied to the coarse residual corrects xc
@@ -536,7 +547,7 @@ class AMG:
             be.spmv(Lc.Mop, Lc.xs, Lc.b_, alpha=-1.0, beta=1.0, y0=Lc.bs)
             xc = self._cycle(i + 1, Lc.b_)
             xc.add_(Lc.xs)
-        be.spmv(L.P, xc, L.x, alpha=1.0, beta=1.0, y0=L.x)             # x += P xc
+        be.spmv(L.P_op, xc, L.x, alpha=1.0, beta=1.0, y0=L.x)          # x += P xc
         self._smooth(L, b, L.x, first_zero=False)
         return L.x
 

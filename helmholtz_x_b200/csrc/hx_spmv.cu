@@ -101,10 +101,11 @@ __global__ void diag_pos_kernel(int n, const int* __restrict__ indptr, const int
 
 // ---- SELL-32: one thread per row, column-major inside a 32-row slice ----------
 // MODE 0: y = acc; 1: y = alpha*acc + beta*y0; 2: Jacobi xout = xin + omega*dinv*(b - acc)
-template <int UNROLL, int MINB, int MODE, typename V = double2>
+// MV: matrix value type (V, or the real scalar for the real-valued transfer operators of the cycle)
+template <int UNROLL, int MINB, int MODE, typename V = double2, typename MV = V>
 __global__ void __launch_bounds__(256, MINB)
 sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, const int* __restrict__ cols,
-            const V* __restrict__ vals, const int* __restrict__ row_perm, const V* __restrict__ x,
+            const MV* __restrict__ vals, const int* __restrict__ row_perm, const V* __restrict__ x,
             V* __restrict__ y, V alpha, V beta, const V* __restrict__ y0,
             const V* __restrict__ dinv, const V* __restrict__ b, typename scalar_of<V>::type omega) {
     const int slice = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -113,25 +114,25 @@ sell_kernel(int n, int n_slices, const long long* __restrict__ slice_ptr, const 
     const long long base = slice_ptr[slice];
     const int width = (int)((slice_ptr[slice + 1] - base) >> 5);
     const int* c = cols + base + lane;
-    const V* v = vals + base + lane;
+    const MV* v = vals + base + lane;
     V acc[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) acc[u] = vzero<V>();
     int j = 0;
     for (; j + UNROLL <= width; j += UNROLL) {
         int cc[UNROLL];
-        V vv[UNROLL];
+        MV vv[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) cc[u] = ld_stream(c + 32 * (j + u));
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) vv[u] = ld_stream(v + 32 * (j + u));
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) cfma(acc[u], vv[u], __ldg(x + cc[u]));
+        for (int u = 0; u < UNROLL; ++u) mac(acc[u], vv[u], __ldg(x + cc[u]));
     }
     for (; j < width; ++j) {
         const int c0 = ld_stream(c + 32 * j);
-        const V v0 = ld_stream(v + 32 * j);
-        cfma(acc[0], v0, __ldg(x + c0));
+        const MV v0 = ld_stream(v + 32 * j);
+        mac(acc[0], v0, __ldg(x + c0));
     }
 #pragma unroll
     for (int u = 1; u < UNROLL; ++u) acc[0] = cadd(acc[0], acc[u]);
@@ -196,6 +197,16 @@ __global__ void sell_gather_kernel(long long total, const int* __restrict__ src,
     for (; i < total; i += stride) {
         const int s = ld_stream(src + i);
         out[i] = (s >= 0) ? from_c128<V>(csr_vals[s]) : vzero<V>();
+    }
+}
+
+__global__ void sell_gather_real_kernel(long long total, const int* __restrict__ src, const float* __restrict__ csr_vals,
+                                        float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int s = ld_stream(src + i);
+        out[i] = (s >= 0) ? csr_vals[s] : 0.f;
     }
 }
 
@@ -313,14 +324,14 @@ extern "C" int hx_spmv_dz(int n, const int32_t* indptr, const int32_t* indices, 
 }
 
 namespace hx {
-template <int MODE, typename V = double2>
-static int launch_sell(int variant, int n, int n_slices, const long long* sp, const int* cols, const V* vals,
+template <int MODE, typename V = double2, typename MV = V>
+static int launch_sell(int variant, int n, int n_slices, const long long* sp, const int* cols, const MV* vals,
                        const int* perm, const V* x, V* y, V alpha, V beta, const V* y0,
                        const V* dinv, const V* b, typename scalar_of<V>::type omega, cudaStream_t st) {
     const int warps = 8;
     const int grid = ceil_div(n_slices, warps);
 #define HX_SELL(U, MB)                                                                                          \
-    sell_kernel<U, MB, MODE, V><<<grid, warps * 32, 0, st>>>(n, n_slices, sp, cols, vals, perm, x, y, alpha, beta, y0, dinv, b, omega)
+    sell_kernel<U, MB, MODE, V, MV><<<grid, warps * 32, 0, st>>>(n, n_slices, sp, cols, vals, perm, x, y, alpha, beta, y0, dinv, b, omega)
     switch (variant) {
         case 1: HX_SELL(4, 4); break;
         case 2: HX_SELL(4, 6); break;
@@ -427,6 +438,27 @@ extern "C" int hx_spmv_sell_cc(int n, int n_slices, const int64_t* slice_ptr, co
     return launch_sell<1, float2>(variant, n, n_slices, (const long long*)slice_ptr, cols, (const float2*)vals, row_perm,
                                   (const float2*)x, (float2*)y, alpha_h ? h2cf(alpha_h) : one, beta_h ? h2cf(beta_h) : one,
                                   (const float2*)y0, nullptr, nullptr, 0.f, (cudaStream_t)stream);
+}
+
+extern "C" int hx_sell_gather_s(int64_t total, const int32_t* src, const float* csr_vals, float* sell_vals, hx_stream_t stream) {
+    if (total <= 0) return HX_OK;
+    long long blocks = ceil_div<long long>(total, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    sell_gather_real_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(total, src, csr_vals, sell_vals);
+    return check_launch("sell_gather_real_kernel");
+}
+
+extern "C" int hx_spmv_sell_sc(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols, const float* vals,
+                               const int32_t* row_perm, const float* x, float* y, const double* alpha_h,
+                               const double* beta_h, const float* y0, int variant, hx_stream_t stream) {
+    if (n <= 0) return HX_OK;
+    const float2 one = make_float2(1.f, 0.f);
+    if (!alpha_h && !y0)
+        return launch_sell<0, float2, float>(variant, n, n_slices, (const long long*)slice_ptr, cols, vals, row_perm,
+                                             (const float2*)x, (float2*)y, one, one, nullptr, nullptr, nullptr, 0.f, (cudaStream_t)stream);
+    return launch_sell<1, float2, float>(variant, n, n_slices, (const long long*)slice_ptr, cols, vals, row_perm,
+                                         (const float2*)x, (float2*)y, alpha_h ? h2cf(alpha_h) : one, beta_h ? h2cf(beta_h) : one,
+                                         (const float2*)y0, nullptr, nullptr, 0.f, (cudaStream_t)stream);
 }
 
 extern "C" int hx_jacobi_sell_c(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols, const float* vals,

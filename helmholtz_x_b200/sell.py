@@ -38,6 +38,10 @@ class SellPattern:
 
     def values_from_csr(self, csr_vals, out=None, dtype=torch.complex128):
         """SELL-ordered copy of complex128 CSR values (optionally down-converted to complex64)."""
+        if csr_vals.dtype == torch.float32:          # real transfer operator of the complex64 cycle
+            out = out if out is not None else self.be.empty(max(self.total, 1), dtype=torch.float32)
+            _lib.call("hx_sell_gather_s", self.total, self.src.data_ptr(), csr_vals.data_ptr(), out.data_ptr(), self.be.stream)
+            return out
         out = out if out is not None else self.be.empty(max(self.total, 1), dtype=dtype)
         name = "hx_sell_gather_c" if out.dtype == torch.complex64 else "hx_sell_gather"
         _lib.call(name, self.total, self.src.data_ptr(), csr_vals.data_ptr(), out.data_ptr(), self.be.stream)
@@ -71,7 +75,7 @@ class SellMatrix:
         y0p = None
         if beta is not None:
             y0p = (y0 if y0 is not None else y).data_ptr()
-        name = "hx_spmv_sell_cc" if self.vals.dtype == torch.complex64 else "hx_spmv_sell_zz"
+        name = {torch.complex64: "hx_spmv_sell_cc", torch.float32: "hx_spmv_sell_sc"}.get(self.vals.dtype, "hx_spmv_sell_zz")
         _lib.call(name, p.n, p.n_slices, p.slice_ptr.data_ptr(), p.cols.data_ptr(), self.vals.data_ptr(),
                   p.row_perm.data_ptr(), x.data_ptr(), y.data_ptr(), _c2(alpha) if alpha is not None else None,
                   _c2(beta) if beta is not None else None, y0p, self.variant if variant is None else variant, self.be.stream)

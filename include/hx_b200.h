@@ -100,6 +100,14 @@ int hx_jacobi_sell_c(int n, int n_slices, const int64_t* slice_ptr, const int32_
 int hx_jacobi_sweep_c(int n, const int32_t* indptr, const int32_t* indices, const float* vals_c64,
                       const float* dinv_c64, const float* b_c64, const float* xin_c64, float* xout_c64,
                       double omega, int lanes, hx_stream_t stream);
+/* real float32 matrix (the prolongation / restriction operators of the cycle) times complex64 vector in
+ * SELL-32, and the matching value gather */
+int hx_spmv_sell_sc(int n, int n_slices, const int64_t* slice_ptr, const int32_t* cols,
+                    const float* vals_f32, const int32_t* row_perm, const float* x_c64, float* y_c64,
+                    const double* alpha_c128_h, const double* beta_c128_h, const float* y0_c64,
+                    int variant, hx_stream_t stream);
+int hx_sell_gather_s(int64_t total, const int32_t* src, const float* csr_vals_f32, float* sell_vals_f32,
+                     hx_stream_t stream);
 /* SELL value refresh with down-conversion complex128 CSR values -> complex64 SELL values */
 int hx_sell_gather_c(int64_t total, const int32_t* src, const double* csr_vals_c128, float* sell_vals_c64,
                      hx_stream_t stream);
