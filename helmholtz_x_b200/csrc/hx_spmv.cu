@@ -181,8 +181,8 @@ __global__ void sell_fill_kernel(int n, const int* __restrict__ indptr, const in
             cols[p] = indices[start + j];
             if (svals) svals[p] = vals[start + j];
             if (src) src[p] = start + j;
-        } else {                                  // padding: harmless gather of own row, value 0
-            cols[p] = row;
+        } else {                                  // padding: value 0, column = the row's first column (in
+            cols[p] = len > 0 ? indices[start] : 0;   // bounds for rectangular matrices too, e.g. prolongators)
             if (svals) svals[p] = make_double2(0.0, 0.0);
             if (src) src[p] = -1;
         }

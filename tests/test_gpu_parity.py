@@ -257,6 +257,38 @@ def test_spmv_sell_matches_csr():
     assert relmax(y2.cpu().numpy(), (0.6 * dinv * y0).cpu().numpy()) < 1e-14
 
 
+@pytest.mark.parametrize("shape", [(5000, 300), (300, 5000), (4097, 4097)])
+def test_spmv_sell_real_rectangular_transfer_operators(shape):
+    """hx_spmv_sell_sc: float32 matrix (the prolongation / restriction operators of the multigrid cycle,
+    tall and wide) times complex64 vector, with the x += P xc epilogue, against SciPy.  Padding entries
+    must stay inside the column range (a tall matrix has fewer columns than rows)."""
+    import scipy.sparse as sp
+    from helmholtz_x_b200.backend import CsrMatrix
+    from helmholtz_x_b200.sell import SellMatrix, SellPattern
+    b = be()
+    m, n = shape
+    rng = np.random.default_rng(m + n)
+    M = sp.random(m, n, density=min(6.0 / n, 1.0), random_state=rng, format="csr", dtype=np.float32)
+    M.sort_indices()
+    csr = CsrMatrix(m, n, b.asarray(M.indptr, dtype=torch.int32), b.asarray(M.indices, dtype=torch.int32),
+                    b.asarray(M.data, dtype=torch.float32))
+    p = SellPattern(b, csr.indptr, csr.indices, m, n)
+    assert int(p.cols.min()) >= 0 and int(p.cols.max()) < n
+    S = SellMatrix(p, p.values_from_csr(csr.values))
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    y0 = (rng.standard_normal(m) + 1j * rng.standard_normal(m)).astype(np.complex64)
+    xd, yd = b.asarray(x, dtype=torch.complex64), b.asarray(y0, dtype=torch.complex64)
+    out = torch.zeros(m, dtype=torch.complex64, device=b.device)
+    b.spmv(S, xd, out)
+    ref = M.astype(np.float64) @ x.astype(np.complex128)
+    assert relmax(out.cpu().numpy(), ref) < 2e-6
+    b.spmv(S, xd, yd, alpha=1.0, beta=1.0, y0=yd)                 # in place: y += M x
+    assert relmax(yd.cpu().numpy(), y0 + ref) < 2e-6
+    out2 = torch.zeros(m, dtype=torch.complex64, device=b.device)
+    b.spmv(csr, xd, out2)                                         # the CSR kernel it replaces
+    assert relmax(out.cpu().numpy(), out2.cpu().numpy()) < 2e-6
+
+
 def test_fused_operator_apply_with_flame_term():
     case = cases.rijke3d()
     mats = gpu_operators(case)
