@@ -76,16 +76,16 @@ class AcousticMatrices:
             Vasm, c_asm = self.V, self.c
         else:
             # multi-GPU: this rank assembles the cells touching its rows on its sub-mesh
-            if degree != 1:
-                raise NotImplementedError("multi-GPU runs support degree 1 (dof = mesh node) in this round")
             from .dist import DistSpace
-            Vasm = fem.functionspace(part.local_mesh, ("Lagrange", 1))
+            dpart = mesh.dof_partition(degree)            # degree 2: vertex + edge dofs (dist.DofPartition)
+            Vasm = fem.functionspace(part.local_mesh, ("Lagrange", degree))
             cvals = self.c.real_device()                  # restricted on the device, no host round trip
             if isinstance(self.c.function_space, fem.DG0Space):
                 c_asm = fem.Function.from_device(fem.DG0Space(part.local_mesh), part.restrict_cell(cvals))
             else:
                 c_asm = fem.Function.from_device(Vasm, part.restrict_nodal(cvals[:mesh.n_nodes]))
-            bc_dofs = [part.g2l[d][part.g2l[d] >= 0] for d in bc_dofs]
+            g2l_loc = part.g2l if degree == 1 else dpart.g2l_old          # global dof -> dof of the local space
+            bc_dofs = [g2l_loc[d][g2l_loc[d] >= 0] for d in bc_dofs]
         with phase("assembly_fields"):
             a_vals, c_vals = fem.assemble_AC(Vasm, c_asm)
         self.C_nobc_values = c_vals
@@ -102,7 +102,7 @@ class AcousticMatrices:
                 b_vals = fem.assemble_B(Vasm, c_asm, terms)
             info("- Matrix B is assembled.")
         if part is not None:
-            self.V = DistSpace(part, Vasm)
+            self.V = DistSpace(dpart, Vasm)
             a_vals, c_vals = self.V.own_values(a_vals), self.V.own_values(c_vals)
             self.C_nobc_values = self.V.own_values(self.C_nobc_values)
             b_vals = self.V.own_values(b_vals) if b_vals is not None else None

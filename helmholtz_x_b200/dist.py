@@ -114,7 +114,12 @@ class Partition:
             self._d["facet_ids"] = torch.zeros(0, dtype=torch.int64, device=dev)
             self._d["local_facets"] = torch.zeros((0, 3), dtype=torch.int32, device=dev)
         self._h = {}
-        # ---- halo plan: who needs which of my rows --------------------------------------
+        self._halo_plan(owner, ghost, g2l)
+
+    def _halo_plan(self, owner, ghost, g2l):
+        """Who needs which of my rows: every rank learns every ghost list (global ids, grouped by owner) and
+        picks the ids it owns, in the requester's order."""
+        world, rank, dev = self.world, self.rank, owner.device
         self.ghost_owner_counts = torch.bincount(owner[ghost], minlength=world).cpu().numpy().astype(np.int64)
         if world > 1:
             counts = _all_gather_rows(torch.tensor([self.n_ghost, self.n_own], dtype=torch.int64, device=dev).view(1, 2), world).cpu().numpy()
@@ -141,7 +146,7 @@ class Partition:
         return self._d[name]
 
     def __getattr__(self, name):
-        if name in Partition._HOST_VIEWS:
+        if name in type(self)._HOST_VIEWS and name in self.__dict__.get("_d", {}):
             h = self.__dict__["_h"]
             if name not in h:
                 h[name] = self.__dict__["_d"][name].cpu().numpy()
@@ -212,6 +217,59 @@ class Partition:
             v = bufs[q][:int(self.own_counts[q])].cpu().numpy()
             out[ids[q]] = v[:, 0] + 1j * v[:, 1]
         return out
+
+
+class DofPartition(Partition):
+    """Row partition of a degree-2 space on top of the node partition: vertex dofs follow their node, an
+    edge dof belongs to the lower-ranked owner of its two vertices (that rank owns a vertex of the edge, so
+    its sub-mesh holds every cell around the edge and the row it assembles is complete).  The rank's local
+    space numbers [vertices | edges]; `dof_perm` reorders it to [owned | ghosts grouped by owner], the layout
+    every distributed vector and matrix uses.  Same interface as Partition (n_own, l2g, exchange, ...)."""
+
+    _HOST_VIEWS = Partition._HOST_VIEWS + ("dof_perm", "dof_inv_perm", "g2l_old")
+
+    def __init__(self, node_part: Partition, Vglob, Vloc):
+        self.node_part = node_part
+        self.world, self.rank, self.device = node_part.world, node_part.rank, node_part.device
+        dev = self.device
+        nn = node_part.n_global
+        ge = Vglob.edges.to(dev)                                          # (n_edges, 2) global vertex ids, sorted by key
+        gkeys = ge[:, 0] * nn + ge[:, 1]
+        self.n_global = nn + int(ge.shape[0])
+        own_node = node_part.dev("owner")
+        owner = torch.cat([own_node, torch.minimum(own_node[ge[:, 0]], own_node[ge[:, 1]])])
+        l2g_node = node_part.dev("l2g")
+        le = Vloc.edges.to(dev)                                           # local vertex pairs of the local edges
+        ga, gb = l2g_node[le[:, 0]], l2g_node[le[:, 1]]
+        lkeys = torch.minimum(ga, gb) * nn + torch.maximum(ga, gb)
+        gidx = torch.searchsorted(gkeys, lkeys)
+        assert bool((gkeys[gidx.clamp_max(gkeys.numel() - 1)] == lkeys).all()), "a local edge is missing from the global mesh"
+        gl_old = torch.cat([l2g_node, nn + gidx])                         # global dof of every local dof (local order)
+        mine = owner[gl_old] == self.rank
+        own_old = torch.nonzero(mine).reshape(-1)
+        own_old = own_old[torch.sort(gl_old[own_old]).indices]            # owned dofs by ascending global id
+        ghost_old = torch.nonzero(~mine).reshape(-1)
+        ghost_old = ghost_old[torch.sort(owner[gl_old[ghost_old]] * self.n_global + gl_old[ghost_old]).indices]
+        perm = torch.cat([own_old, ghost_old])                            # new local index -> old local index
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(perm.numel(), device=dev)
+        self.n_own, self.n_ghost = int(own_old.numel()), int(ghost_old.numel())
+        l2g = gl_old[perm]
+        g2l = torch.full((self.n_global,), -1, dtype=torch.int64, device=dev)
+        g2l[l2g] = torch.arange(l2g.numel(), device=dev)
+        g2l_old = torch.full((self.n_global,), -1, dtype=torch.int64, device=dev)
+        g2l_old[gl_old] = torch.arange(gl_old.numel(), device=dev)
+        self._d = {"owner": owner, "l2g": l2g, "g2l": g2l, "g2l_old": g2l_old, "dof_perm": perm, "dof_inv_perm": inv,
+                   "cell_ids": node_part.dev("cell_ids")}
+        self._h = {}
+        self._halo_plan(owner, l2g[self.n_own:], g2l)
+        self.local_mesh = node_part.local_mesh
+
+    def restrict_nodal(self, arr):
+        return self.node_part.restrict_nodal(arr)
+
+    def restrict_cell(self, arr):
+        return self.node_part.restrict_cell(arr)
 
 
 class DistMatrix:
@@ -285,7 +343,9 @@ class DistBackend:
 
 class DistSpace:
     """What OperatorSet / AMG need from a function space, for the owned rows of a rank:
-    pattern of the owned rows (columns in local numbering), the diagonal block, coordinates."""
+    pattern of the owned rows (columns in local numbering [owned | ghosts]), the diagonal block,
+    coordinates.  A degree-2 partition carries the permutation from the local space's [vertices | edges]
+    numbering to that layout; for degree 1 the sub-mesh numbering already has it."""
 
     def __init__(self, part: Partition, Vloc):
         self.part, self.Vloc = part, Vloc
@@ -295,15 +355,35 @@ class DistSpace:
         self.n_global = part.n_global
         self.degree = Vloc.degree
         ip, ix = Vloc.pattern()
-        self.nnz_own = int(ip[part.n_own])
-        self._pattern = (ip[:part.n_own + 1].contiguous(), ix[:self.nnz_own].contiguous())
-        self.dof_coords = Vloc.dof_coords[:part.n_own].contiguous()
-        mask = self._pattern[1] < part.n_own
+        dev = ip.device
+        n_own = part.n_own
+        if isinstance(part, DofPartition):
+            perm, inv = part.dev("dof_perm").to(dev), part.dev("dof_inv_perm").to(dev)
+            ipl = ip.long()
+            old_rows = perm[:n_own]
+            cnt = (ipl[1:] - ipl[:-1])[old_rows]
+            ptr = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
+            ptr[1:] = torch.cumsum(cnt, 0)
+            total = int(ptr[-1])
+            pos = torch.repeat_interleave(ipl[old_rows] - ptr[:-1], cnt, output_size=total) + torch.arange(total, device=dev)
+            rows = torch.repeat_interleave(torch.arange(n_own, device=dev), cnt, output_size=total)
+            cols = inv[ix[pos].long()]
+            order = torch.sort(rows * int(perm.numel()) + cols).indices          # columns of a row ascending again
+            self._value_perm = pos[order]
+            self._pattern = (ptr.to(torch.int32).contiguous(), cols[order].to(torch.int32).contiguous())
+            self.nnz_own = total
+            self.dof_coords = Vloc.dof_coords[old_rows].contiguous()
+        else:
+            self._value_perm = None
+            self.nnz_own = int(ip[n_own])
+            self._pattern = (ip[:n_own + 1].contiguous(), ix[:self.nnz_own].contiguous())
+            self.dof_coords = Vloc.dof_coords[:n_own].contiguous()
+        mask = self._pattern[1] < n_own
         self.diag_sel = torch.nonzero(mask).reshape(-1)
-        rows = torch.repeat_interleave(torch.arange(part.n_own, device=ip.device),
+        rows = torch.repeat_interleave(torch.arange(n_own, device=dev),
                                        (self._pattern[0][1:] - self._pattern[0][:-1]).long())
-        counts = torch.bincount(rows[mask], minlength=part.n_own)
-        dptr = torch.zeros(part.n_own + 1, dtype=torch.int64, device=ip.device)
+        counts = torch.bincount(rows[mask], minlength=n_own)
+        dptr = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
         dptr[1:] = torch.cumsum(counts, 0)
         self._diag_pattern = (dptr.to(torch.int32).contiguous(), self._pattern[1][mask].contiguous())
         self._xbuf = None
@@ -329,7 +409,16 @@ class DistSpace:
         return self._pattern
 
     def own_values(self, full_values):
+        """Values of the owned rows (this space's pattern order) from values on the local space's pattern."""
+        if self._value_perm is not None:
+            return full_values[self._value_perm].contiguous()
         return full_values[:self.nnz_own].contiguous()
+
+    def own_vector(self, local_vector):
+        """Owned entries (distributed layout) of a vector in the local space's numbering."""
+        if isinstance(self.part, DofPartition):
+            return local_vector[self.part.dev("dof_perm").to(local_vector.device)[:self.part.n_own]].contiguous()
+        return local_vector[:self.part.n_own].contiguous()
 
     def matrix(self, values):
         local = CsrMatrix(self.part.n_own, self.part.n_loc, self._pattern[0], self._pattern[1], values)

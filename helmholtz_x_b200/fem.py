@@ -100,6 +100,7 @@ class Mesh:
         self._volumes = None
         self._facet_cell = None
         self._part = None
+        self._dof_parts = {}
 
     def __getattr__(self, name):
         lazy = Mesh._LAZY.get(name)
@@ -125,6 +126,19 @@ class Mesh:
                                        part.dev("local_facets"), self.facet_tagsd[part.dev("facet_ids")], backend=self.be)
             self._part = part
         return self._part
+
+    def dof_partition(self, degree):
+        """Row partition of the degree-`degree` space over the process group: the node partition for degree 1,
+        dist.DofPartition (vertex + edge dofs) for degree 2; None on one GPU."""
+        part = self.partition()
+        if part is None or degree == 1:
+            return part
+        if degree not in self._dof_parts:
+            from . import dist as hxdist
+            with phase("partition"):
+                self._dof_parts[degree] = hxdist.DofPartition(part, functionspace(self, ("Lagrange", degree)),
+                                                              functionspace(part.local_mesh, ("Lagrange", degree)))
+        return self._dof_parts[degree]
 
     # -- colouring (device: Jones-Plassmann rounds with fixed priorities, hx_color_cells) ------------
     @staticmethod

@@ -23,11 +23,12 @@ class FlameMatrix:
         self.tol = tol
         # multi-GPU: this rank works on its sub-mesh and keeps the entries of the rows it owns
         self.part = mesh.partition()
+        self.dpart = mesh.dof_partition(degree)           # rows of the degree-`degree` space over the ranks
         self.amesh = mesh if self.part is None else self.part.local_mesh
         self.V = fem.functionspace(self.amesh, ("Lagrange", degree))
         self.gdim = 3
-        self.global_size = fem.functionspace(mesh, ("Lagrange", degree)).n if self.part is None else mesh.n_nodes
-        self.local_size = self.V.n if self.part is None else self.part.n_own
+        self.global_size = fem.functionspace(mesh, ("Lagrange", degree)).n if self.part is None else self.dpart.n_global
+        self.local_size = self.V.n if self.part is None else self.dpart.n_own
         self._D_ij = None
         self._D_ij_adj = None
         self._D = None
@@ -52,10 +53,17 @@ class FlameMatrix:
     def indices_and_values(self, dense):
         """Threshold |v| < tol -> 0 and compact to (dof, value) (flame_matrices.py:61-73)."""
         fem.threshold(self.V.be, dense, self.tol)
-        if self.part is not None:
-            dense = dense[:self.part.n_own]              # ghost rows are incomplete and belong to other ranks
+        if self.part is not None:                        # ghost rows are incomplete and belong to other ranks
+            dense = self._own(dense)
         idx = torch.nonzero(dense).reshape(-1)
         return idx.cpu().numpy().astype(np.int32), dense[idx].cpu().numpy()
+
+    def _own(self, v):
+        """Entries of the rows this rank owns, in the distributed layout, from a vector of the local space."""
+        n_own = self.dpart.n_own
+        if self.degree == 1:
+            return v[:n_own]
+        return v[self.dpart.dev("dof_perm").to(v.device)[:n_own]].contiguous()
 
     def _local(self, f):
         """Coefficient restricted to this rank's sub-mesh (identity on one GPU)."""
@@ -156,9 +164,12 @@ class PointwiseFlameMatrix(FlameMatrix):
                 vals = dz[flame] / self.rho_u
                 vals = np.where(np.abs(vals) < self.tol, 0.0, vals)
                 keep = vals != 0.0
+                dofs = cell_dofs[flame]
                 if self.part is not None:
-                    keep &= cell_dofs[flame] < self.part.n_own
-                rights.append((cell_dofs[flame][keep].astype(np.int32), vals[keep]))
+                    if self.degree != 1:
+                        dofs = self.dpart.dof_inv_perm[dofs]         # local space numbering -> [owned | ghosts]
+                    keep &= dofs < self.dpart.n_own
+                rights.append((dofs[keep].astype(np.int32), vals[keep]))
             info("- Matrix contribution of flame " + str(flame) + " is computed.")
         self._h_dev = None
         self._set(lefts, rights, problem_type)

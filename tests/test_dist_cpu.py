@@ -212,6 +212,105 @@ def _worker(rank, world, port, ordering, q, hierarchy=False):
         dist.destroy_process_group()
 
 
+def _p2_worker(rank, world, port, q):
+    """Degree 2 over two ranks: dist.DofPartition (vertex + edge dofs), permuted local space, SpMV, eigen-solve."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["RANK"] = str(rank)
+    os.environ["HX_DIST_HIERARCHY"] = "1"
+    _single_thread()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sp
+        from helmholtz_x_b200 import eigensolvers, fem
+        from helmholtz_x_b200.dist import DistSpace, DofPartition, Partition
+        from helmholtz_x_b200.operators import Mat, OperatorSet
+        from oracle.host_backend import HostBackend
+        from oracle import hx_oracle as ox
+        case = cases.rijke3d()
+        case["degree"] = 2
+        m = case.mesh
+        ops_o = cases.oracle_operators(case, passive=True)
+        be = HostBackend()
+        gmesh = fem.Mesh(m.x, m.cells, m.cell_tags, m.facets, m.facet_tags, backend=be)
+        part = Partition(gmesh.xd, gmesh.cellsd, world, rank, "morton", gmesh.facetsd)
+        part.local_mesh = fem.Mesh(gmesh.xd[part.dev("l2g")], part.dev("local_cells"), gmesh.cell_tagsd[part.dev("cell_ids")],
+                                   part.dev("local_facets"), gmesh.facet_tagsd[part.dev("facet_ids")], backend=be)
+        Vglob, Vloc = fem.FunctionSpace(gmesh, 2), fem.FunctionSpace(part.local_mesh, 2)
+        assert Vglob.n == ops_o.A.shape[0]
+        dpart = DofPartition(part, Vglob, Vloc)
+        # every global dof is owned exactly once
+        owned = [None] * world
+        dist.all_gather_object(owned, dpart.l2g[:dpart.n_own])
+        allo = np.concatenate(owned)
+        assert len(allo) == Vglob.n and len(np.unique(allo)) == Vglob.n
+        assert np.all(np.diff(dpart.l2g[:dpart.n_own]) > 0)                       # ascending global ids
+        assert dpart.n_ghost > 0 and (dpart.owner[dpart.l2g[dpart.n_own:]] != rank).all()
+        gl_old = dpart.l2g[dpart.dof_inv_perm]                                    # global dof of every dof of the local space
+
+        class FakeV:
+            degree = 2
+
+            def __init__(self, A):
+                self.be = be
+                sub = sp.csr_matrix(A)[gl_old][:, gl_old].tocsr()
+                sub.sort_indices()
+                self.sub = sub
+                self._p = (torch.from_numpy(sub.indptr.astype(np.int32)), torch.from_numpy(sub.indices.astype(np.int32)))
+                self.dof_coords = Vloc.dof_coords
+
+            def pattern(self):
+                return self._p
+        pat_src = abs(ops_o.A) + abs(ops_o.C)
+        V = FakeV(pat_src)
+
+        def vals(Mg):
+            sub = sp.csr_matrix(Mg)[gl_old][:, gl_old].tocsr()
+            P = sp.csr_matrix((np.arange(1, V.sub.nnz + 1), V.sub.indices, V.sub.indptr), shape=V.sub.shape)
+            out = np.zeros(V.sub.nnz)
+            coo = sub.tocoo()
+            out[np.asarray(P[coo.row, coo.col]).ravel().astype(np.int64) - 1] = coo.data.real
+            return torch.from_numpy(out)
+        space = DistSpace(dpart, V)
+        ops = OperatorSet(space, space.own_values(vals(ops_o.A)), space.own_values(vals(ops_o.C)), None)
+        A, C = Mat(ops, {"A": 1.0}), Mat(ops, {"C": 1.0})
+        rng = np.random.default_rng(0)
+        xg = rng.standard_normal(Vglob.n) + 1j * rng.standard_normal(Vglob.n)
+        xl = torch.from_numpy(ops.to_local(xg))
+        yl = torch.zeros(dpart.n_own, dtype=torch.complex128)
+        A.apply(xl, yl)
+        ref = (ops_o.A @ xg)[dpart.l2g[:dpart.n_own]]
+        assert np.abs(yl.numpy() - ref).max() < 1e-12 * np.abs(ref).max()
+        assert np.allclose(ops.to_global(xl), xg)
+        E = eigensolvers.eps_solver(A, C, case.target, nev=2)
+        Eo = ox.eps_solve(ops_o.A, -ops_o.C, case.target ** 2, 2)
+        lam = np.array([E.getEigenvalue(i) for i in range(2)])
+        for lo in Eo.eigenvalues[:2]:
+            assert min(abs(lam - lo)) < 1e-8 * max(abs(lo), 1.0) + 1e-3, (lam, Eo.eigenvalues)
+        assert ops.hierarchy() is not None
+        q.put((rank, "ok", ops.stats["inner_iterations"]))
+    except Exception:      # noqa: BLE001
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_degree_two_partition():
+    """P2 across ranks: edge dofs owned by the lower-ranked owner of their vertices (dist.DofPartition)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_p2_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in res:
+        assert status == "ok", f"rank {rank}: {info}"
+
+
 @pytest.mark.parametrize("ordering,hierarchy", [("morton", False), ("morton", True)])
 def test_two_rank_partitioned_solve_matches_goldens(ordering, hierarchy):
     """'input' ordering is only meaningful for meshes whose node order is already local

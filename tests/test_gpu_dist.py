@@ -31,6 +31,7 @@ def test_two_gpus_peer_transport_and_golden_fpi():
         assert all(v == 0 for v in r["unit"].values()), r["unit"]          # bitwise: halo values and rank-ordered sums
         assert r["rijke3d"]["max_abs_diff_vs_log"] < 2e-8, r["rijke3d"]     # the log prints 8 decimals
         assert r["annulus"]["rel_diff_vs_eigenvalues_dir"] < 1e-8
+        assert r["rijke3d_p2"]["rel_diff_vs_oracle"] < 1e-8                 # degree 2 across ranks (dist.DofPartition)
         assert r["rijke3d"]["distributed_levels"] >= 1 and r["rijke3d"]["cycle_in_graph"]
     assert out[0]["annulus"]["omega"] == out[1]["annulus"]["omega"]          # replicated host logic: bit for bit
 

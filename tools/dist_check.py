@@ -85,7 +85,7 @@ def unit_checks(rank, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="rijke3d,annulus")
+    ap.add_argument("--cases", default="rijke3d,annulus,rijke3d_p2")
     ap.add_argument("--no-unit", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -106,10 +106,35 @@ def main():
     out = {"world": world, "transport": peer.transport()}
     if not args.no_unit and peer.transport() == "peer":
         out["unit"] = unit_checks(rank, world)
-    table = {"rijke3d": (cases.rijke3d, "rijke3d_active_fpi"), "annulus": (cases.annulus, "annulus_fpi_direct")}
+    def rijke3d_p2():
+        c = cases.rijke3d()
+        c["degree"] = 2
+        return c
+    table = {"rijke3d": (cases.rijke3d, "rijke3d_active_fpi"), "annulus": (cases.annulus, "annulus_fpi_direct"),
+             "rijke3d_p2": (rijke3d_p2, None)}
     for name in [c for c in args.cases.split(",") if c]:
         mk, gkey = table[name]
         case = mk()
+        if gkey is None:
+            # degree 2 across ranks (dist.DofPartition): no reference golden exists for P2, the
+            # CPU oracle's fixed-point iteration on the same mesh is the target
+            from oracle import hx_oracle as ox
+            quiet = io.StringIO()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(quiet):
+                mats = gpu_operators(case)
+                D = gpu_flame(case)
+                D.assemble_submatrices()
+                E = fixed_point_iteration(mats, D, case.target, nev=2, i=0, tol=1e-8)
+                omega, p = normalize_eigenvector(mats.mesh, E, 0, degree=2, matrices=mats, print_eigs=False)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            Eo, _ = ox.fixed_point_iteration(cases.oracle_operators(case), cases.oracle_flame(case), case.target, nev=2, i=0, tol=1e-8)
+            out[name] = {"seconds": round(dt, 3), "omega": [omega.real, omega.imag], "n_own": mats.ops.n, "n_global": mats.ops.n_global,
+                         "rel_diff_vs_oracle": abs(omega - Eo.omega(0)) / abs(Eo.omega(0)),
+                         "stats": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in mats.ops.stats.items()}}
+            del mats, D, E
+            continue
         quiet = io.StringIO()
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(quiet):
