@@ -37,6 +37,9 @@ RECORD_DOFS = int(os.environ.get("HX_BENCH_RECORD_DOFS", 10_000_000))
 # size at which BOTH arms run (the CPU oracle's sparse LU takes ~10-30 s there)
 ANCHOR_DOFS = int(os.environ.get("HX_BENCH_ANCHOR_DOFS", 16_000))
 CPU_THREADS = int(os.environ.get("HX_BENCH_CPU_THREADS", 1))      # see cpu_sample
+# wall-clock budget of one bench.py process: the scaling run kills a rank count after 870 s, so the extras after the
+# timed loop (per-phase step, 10M record, anchor) only run while they still fit
+BUDGET_S = float(os.environ.get("HX_BENCH_BUDGET_S", 780))
 TARGET = 3225.120 + 481.0j            # fullAnnulus/active_fpi.py:40
 NEV, FPI_TOL = 4, 1e-3                # active_fpi.py:41
 
@@ -364,7 +367,18 @@ def run_b200(args):
                        "ok": bool(rel < 1e-8), "source": "tests/golden/bench_omega.json"}
     # ---- per-phase breakdown: ONE extra untimed step with a device synchronisation at every phase boundary
     phase_report = None
-    if not args.no_phases:
+
+    def fits(seconds):
+        elapsed = time.perf_counter() - t_job0
+        if world > 1:                     # one decision for all ranks (the extra step is collective)
+            import torch.distributed as dist
+            t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed = float(t[0])
+        return elapsed + seconds < BUDGET_S
+    if not args.no_phases and not fits(1.3 * e2e_s + 5):
+        phase_report = {"skipped": f"would not fit the {BUDGET_S:.0f} s budget of one bench.py process"}
+    elif not args.no_phases:
         phases.enable(True)
         tp0 = time.perf_counter()
         with contextlib.redirect_stdout(quiet):
@@ -412,10 +426,11 @@ def run_b200(args):
     torch.cuda.empty_cache()
     # ---- the same step, once, at the size the target is quoted on (10 M DoF), in this very run -------------
     record = None
-    elapsed = time.perf_counter() - t_job0
-    if args.record_dofs and world == 1 and args.record_dofs > args.dofs:
-        if elapsed > 600:
-            record = {"skipped": f"{elapsed:.0f} s already spent; the scaling run's per-N limit is 870 s"}
+    if args.record_dofs and world == 1 and args.record_dofs > 1.05 * args.dofs:
+        est = 25 + 1.4 * step_s * (args.record_dofs / args.dofs) ** 1.1
+        if not fits(est + (60 if args.anchor_dofs else 0)):
+            record = {"skipped": f"{time.perf_counter() - t_job0:.0f} s spent, the record needs about {est:.0f} s more and one "
+                                 f"bench.py process has {BUDGET_S:.0f} s (the scaling run's per-N limit is 870 s)"}
         else:
             try:
                 record = record_step(args.record_dofs, args.degree, barrier, quiet, peak)
@@ -424,7 +439,9 @@ def run_b200(args):
             torch.cuda.empty_cache()
     # ---- anchor: both arms on one size --------------------------------------------------------------------
     anchor = None
-    if args.anchor_dofs and world == 1 and rank == 0 and not args.no_cpu_baseline:
+    if args.anchor_dofs and world == 1 and rank == 0 and not args.no_cpu_baseline and not fits(60):
+        anchor = {"skipped": f"would not fit the {BUDGET_S:.0f} s budget of one bench.py process"}
+    elif args.anchor_dofs and world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
             anchor = anchor_both_arms(args.anchor_dofs, args.degree, barrier, quiet)
         except Exception as ex:              # noqa: BLE001
