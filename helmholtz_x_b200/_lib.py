@@ -62,6 +62,7 @@ SIGNATURES = {
     "hx_diag_positions": [i32, vp, vp, vp, vp],
     "hx_dense_inverse": [i32, vp, vp, vp],
     "hx_dense_gemv": [i32, vp, vp, vp, vp],
+    "hx_amg_tail": [vp, vp, vp],
     "hx_spgemm_symbolic": [i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "hx_spgemm_numeric": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_dof_cell_count": [i64, i32, vp, i32, vp, vp],

@@ -128,6 +128,20 @@ class Level:
     pass
 
 
+import ctypes as _C
+
+
+class TailDesc(_C.Structure):
+    """hx_tail_desc (include/hx_b200.h)."""
+    _fields_ = [("n", _C.c_int32), ("nc", _C.c_int32), ("nu", _C.c_int32), ("pad_", _C.c_int32),
+                ("a_ptr", _C.c_void_p), ("a_idx", _C.c_void_p), ("a_val", _C.c_void_p), ("dinv", _C.c_void_p),
+                ("r_ptr", _C.c_void_p), ("r_idx", _C.c_void_p), ("r_val", _C.c_void_p),
+                ("p_ptr", _C.c_void_p), ("p_idx", _C.c_void_p), ("p_val", _C.c_void_p),
+                ("coarse_inv", _C.c_void_p), ("omega", _C.c_float * 4),
+                ("buf0", _C.c_void_p), ("buf1", _C.c_void_p), ("r", _C.c_void_p), ("bc", _C.c_void_p), ("xc", _C.c_void_p),
+                ("barrier", _C.c_void_p)]
+
+
 def filter_prolongator(P: CsrMatrix, theta):
     """Drop the entries of a smoothed prolongator below theta * (largest entry of the row) and rescale the
     kept ones so that every row keeps its sum (constants stay in the range of P).  The Galerkin operators
@@ -480,7 +494,38 @@ class AMG:
         info = be.dense_inverse(dense)
         self.coarse_inv = dense
         self._coarse_info = info
+        self._tail = self._tail_descriptor()
         return self
+
+    def _tail_descriptor(self):
+        """Descriptor of the fused cycle tail (last smoothed level + dense coarsest solve, hx_amg_tail), or None
+        when it does not apply: one level, complex128 cycle, that level stored as SELL, or HX_AMG_TAIL=0."""
+        if (len(self.levels) < 2 or not self.single or not getattr(self.be, "supports_tail", False)
+                or os.environ.get("HX_AMG_TAIL", "1") == "0"):
+            return None
+        L, Lc = self.levels[-2], self.levels[-1]
+        if getattr(L.Mop, "is_sell", False) or L.Mop.values.dtype != torch.complex64 or not 1 <= L.nu <= 4:
+            return None
+        if L.P.values.dtype != torch.float32 or L.R.values.dtype != torch.float32:
+            return None
+        d = TailDesc()
+        d.n, d.nc, d.nu = L.n, Lc.n, L.nu
+        d.a_ptr, d.a_idx, d.a_val = L.Mop.indptr.data_ptr(), L.Mop.indices.data_ptr(), L.Mop.values.data_ptr()
+        d.dinv = L.dinv_w.data_ptr()
+        d.r_ptr, d.r_idx, d.r_val = L.R.indptr.data_ptr(), L.R.indices.data_ptr(), L.R.values.data_ptr()
+        d.p_ptr, d.p_idx, d.p_val = L.P.indptr.data_ptr(), L.P.indices.data_ptr(), L.P.values.data_ptr()
+        d.coarse_inv = self.coarse_inv.data_ptr()
+        for s_, om in enumerate(L.omegas):
+            d.omega[s_] = float(om)
+        if not hasattr(L, "tail_bar"):
+            L.tail_bar = torch.zeros(2, dtype=torch.int32, device=L.dinv.device)
+            L.tail_x, L.tail_t = L.x, L.t                # fixed roles: the result always lands in tail_x
+        swaps = 2 * L.nu - 1
+        d.buf0, d.buf1 = (L.tail_t.data_ptr(), L.tail_x.data_ptr()) if swaps % 2 else (L.tail_x.data_ptr(), L.tail_t.data_ptr())
+        d.r, d.bc, d.xc = L.r.data_ptr(), Lc.b64.data_ptr(), Lc.x64.data_ptr()
+        d.barrier = L.tail_bar.data_ptr()
+        self._tail_keep = (L.Mop, L.dinv_w, self.coarse_inv)     # the descriptor holds raw pointers
+        return d
 
     def fine_matrix(self):
         return self.levels[0].M
@@ -527,6 +572,10 @@ class AMG:
         """Solve approximately M_i x = b; result in self.levels[i].x."""
         be = self.be
         L = self.levels[i]
+        if i == len(self.levels) - 2 and getattr(self, "_tail", None) is not None:
+            be.amg_tail(self._tail, b)                    # this level and the coarsest one in one persistent kernel
+            L.x, L.t = L.tail_x, L.tail_t
+            return L.x
         if i == len(self.levels) - 1:
             if self.single:                       # the coarsest solve stays in double precision
                 L.b64.copy_(b)

@@ -89,6 +89,7 @@ class CudaBackend:
     supports_spgemm = True       # hx_spgemm_* for the multigrid set-up
     supports_graphs = True       # CUDA-graph capture of fixed launch sequences (the multigrid cycle)
     supports_pipelining = True   # Hessenberg columns return through a pinned buffer on a copy stream
+    supports_tail = True         # last smoothed level + coarsest solve of the cycle as one persistent kernel
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():
@@ -229,6 +230,10 @@ class CudaBackend:
             _lib.call(name, M.n_rows, M.indptr.data_ptr(), M.indices.data_ptr(), M.values.data_ptr(),
                       dinv.data_ptr(), b.data_ptr(), xin.data_ptr(), xout.data_ptr(), float(omega), M.lanes, self.stream)
         return xout
+
+    def amg_tail(self, desc, b):
+        """Run the fused tail of the multigrid cycle (amg.TailDesc) on the right-hand side b (complex64)."""
+        _lib.call("hx_amg_tail", C.byref(desc), b.data_ptr(), self.stream)
 
     def dense_inverse(self, A):
         """In-place inverse of a column-major n x n complex matrix; returns info tensor (0 = ok)."""

@@ -185,6 +185,26 @@ int hx_diag_positions(int n, const int32_t* indptr, const int32_t* indices, int3
 int hx_dense_inverse(int n, double* a_c128_colmajor, int32_t* info_dev, hx_stream_t stream);
 int hx_dense_gemv(int n, const double* a_c128_colmajor, const double* x_c128, double* y_c128, hx_stream_t stream);
 
+/* The tail of the multigrid cycle as ONE persistent kernel (grid-wide barriers instead of kernel boundaries):
+ * on the last smoothed level (complex64 CSR, n rows) nu pre-sweeps (the first from zero), residual, restriction
+ * (float32 CSR, nc rows), dense coarsest solve xc = Ainv bc (complex128 column-major inverse), prolongation
+ * (float32 CSR, n rows), nu post-sweeps.  omega[s] = damping of sweep s (pre and post alike).  The result ends in
+ * buf0 when the number of buffer swaps 2 nu - 1 is even, else in buf1 (the host knows nu).
+ * barrier: device uint32[2], zero-initialised, private to this descriptor. */
+typedef struct {
+    int32_t n, nc, nu, pad_;
+    const int32_t* a_ptr; const int32_t* a_idx; const float* a_val;      /* level operator, complex64 values */
+    const float* dinv;                                                   /* complex64 */
+    const int32_t* r_ptr; const int32_t* r_idx; const float* r_val;      /* restriction, float32 */
+    const int32_t* p_ptr; const int32_t* p_idx; const float* p_val;      /* prolongation, float32 */
+    const double* coarse_inv;                                            /* complex128, nc x nc column-major */
+    float omega[4];
+    void* buf0; void* buf1; void* r;                                     /* complex64, n each */
+    void* bc; void* xc;                                                  /* complex128, nc each */
+    void* barrier;
+} hx_tail_desc;
+int hx_amg_tail(const hx_tail_desc* desc_h, const float* b_c64, hx_stream_t stream);
+
 /* multigrid set-up: C = A * B on CSR (real double), one warp per row.  symbolic: distinct
  * column count per row (write_cols=0; -1 = more than 2048 columns, caller falls back) or the
  * sorted columns (write_cols=1); numeric: deterministic accumulation into a given pattern. */

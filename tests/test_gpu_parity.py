@@ -470,6 +470,32 @@ def test_amg_vcycle_matches_host_double_and_gmres_converges():
     assert mats.ops.stats["inner_iterations"] <= 60, mats.ops.stats
 
 
+def test_amg_fused_tail_matches_the_kernel_by_kernel_cycle(monkeypatch):
+    """hx_amg_tail (last smoothed level + dense coarsest solve as one persistent kernel with grid barriers)
+    against the same cycle launched kernel by kernel: complex64 round-off apart, V- and W-cycle, repeated
+    applications (the barrier state persists across launches)."""
+    from helmholtz_x_b200.amg import AMG
+    case = cases.annulus()
+    mats = gpu_operators(case)
+    ops = mats.ops
+    pat = ops.space.matrix
+    s = case.target
+    outs = {}
+    for w_from in (None, 1):
+        for tail in ("0", "1"):
+            monkeypatch.setenv("HX_AMG_TAIL", tail)
+            mg = AMG(be(), pat(ops.base["A"]), pat(ops.base["C"]), pat(ops.base["B"]), ops.space.dof_coords, w_from=w_from or "off")
+            mg.set_shift(1.0, s, s ** 2)
+            assert (mg._tail is not None) == (tail == "1") and len(mg.levels) >= 3
+            rng = np.random.default_rng(5)
+            v = be().asarray(rng.standard_normal(ops.n) + 1j * rng.standard_normal(ops.n), dtype=torch.complex128)
+            y = be().zeros(ops.n)
+            for _ in range(3):
+                mg.apply(v, y)
+            outs[(w_from, tail)] = y.cpu().numpy().copy()
+        assert relmax(outs[(w_from, "1")], outs[(w_from, "0")]) < 5e-5, w_from
+
+
 @pytest.mark.parametrize("precision,sell_min_rows,graph", [("single", 1000, True), ("double", 1000, True),
                                                            ("single", 10 ** 9, True), ("single", 1000, False)])
 def test_amg_precision_modes_reach_full_accuracy(precision, sell_min_rows, graph, monkeypatch):
