@@ -499,9 +499,13 @@ class AMG:
 
     def _tail_descriptor(self):
         """Descriptor of the fused cycle tail (last smoothed level + dense coarsest solve, hx_amg_tail), or None
-        when it does not apply: one level, complex128 cycle, that level stored as SELL, or HX_AMG_TAIL=0."""
+        when it does not apply: one level, complex128 cycle, that level stored as SELL, or not asked for.
+        OFF by default (HX_AMG_TAIL=1 switches it on): measured on B200 (profiles/r2_tail_*.json) one visit of the
+        tail drops from 82 to 42 us at 1 M DoF (1950 rows) but rises from 81 to 105 us at 5 M DoF (9760 rows x 180
+        nonzeros: one CTA per SM hides too little latency), and the graph-replayed cycle is slower in both cases
+        (466 -> 543 us, 1800 -> 2125 us); whole step 2.98 -> 3.23 s and 12.8 -> 13.8 s.  Kept as a tested option."""
         if (len(self.levels) < 2 or not self.single or not getattr(self.be, "supports_tail", False)
-                or os.environ.get("HX_AMG_TAIL", "1") == "0"):
+                or os.environ.get("HX_AMG_TAIL", "0") != "1"):
             return None
         L, Lc = self.levels[-2], self.levels[-1]
         if getattr(L.Mop, "is_sell", False) or L.Mop.values.dtype != torch.complex64 or not 1 <= L.nu <= 4:

@@ -483,7 +483,7 @@ def test_amg_fused_tail_matches_the_kernel_by_kernel_cycle(monkeypatch):
     outs = {}
     for w_from in (None, 1):
         for tail in ("0", "1"):
-            monkeypatch.setenv("HX_AMG_TAIL", tail)
+            monkeypatch.setenv("HX_AMG_TAIL", tail)           # off by default (slower in the graph-replayed cycle)
             mg = AMG(be(), pat(ops.base["A"]), pat(ops.base["C"]), pat(ops.base["B"]), ops.space.dof_coords, w_from=w_from or "off")
             mg.set_shift(1.0, s, s ** 2)
             assert (mg._tail is not None) == (tail == "1") and len(mg.levels) >= 3
