@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-DEFAULT_DOFS = int(os.environ.get("HX_BENCH_DOFS", 5_000_000))
+DEFAULT_DOFS = int(os.environ.get("HX_BENCH_DOFS", 8_000_000))
 # one extra step at the size BASELINE's target is quoted on, measured in the same run (N=1 only)
 RECORD_DOFS = int(os.environ.get("HX_BENCH_RECORD_DOFS", 10_000_000))
 # size at which BOTH arms run (the CPU oracle's sparse LU takes ~10-30 s there)
@@ -456,8 +456,9 @@ def run_b200(args):
                    "step": "CSR pattern + colouring + assemble A,B,C + D + fixed-point omega iteration (PEP shift-invert "
                            "Krylov-Schur) + eigenvector normalisation",
                    "dofs": n_dofs, "cells": n_cells,
-                   "size_choice": "largest size whose warm-up + timed steps + 10M record + anchor fit the scaling run's "
-                                  "870 s per-N limit on one GPU; the 10M-DoF step is measured once in this run (record_10m)",
+                   "size_choice": "8M DoF: the largest round size whose 5 warm-up + 20 timed steps (21 s each on one B200) plus the "
+                                  "10M record and the anchor fit the scaling run's 870 s per-N limit; the 10M-DoF step (27 s: 25 "
+                                  "of them do not fit) is measured once in this same run (record_10m)",
                    "l2": "the step streams GBs per iteration; the roofline loop re-reads the whole matrix every launch",
                    "multi_gpu": ("rows partitioned over ranks (Morton chunks), halo exchange + Gram all-reduces over NVLink "
                                  "peer memory, row-distributed multigrid cycle") if world > 1 else "single"},

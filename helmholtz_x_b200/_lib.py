@@ -65,6 +65,7 @@ SIGNATURES = {
     "hx_amg_tail": [vp, vp, vp],
     "hx_spgemm_symbolic": [i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "hx_spgemm_numeric": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "hx_spgemm_numeric_small": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "hx_dof_cell_count": [i64, i32, vp, i32, vp, vp],
     "hx_dof_cell_fill": [i64, i32, vp, i32, vp, vp, vp, vp],
     "hx_pattern_rows": [i32, i32, vp, vp, vp, vp, vp, vp, i32, vp],

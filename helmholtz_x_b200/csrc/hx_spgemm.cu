@@ -10,22 +10,24 @@
 
 namespace hx {
 
-constexpr int kSgWarps = 2;
-constexpr int kSgHash = 4096;       // hash slots per warp
-constexpr int kSgCap = 2048;        // max distinct columns per C row
-
+// Two size classes: rows of the fine levels have a few dozen distinct columns -- a 1024-slot table and a
+// 512-entry row buffer per warp let 8 warps share a CTA (24 KB) and several CTAs an SM; the dense coarse
+// rows need the large class (4096 / 2048, 2 warps per CTA).  The host tries the small class first and
+// falls back on overflow.
+template <int HASH>
 __device__ __forceinline__ bool sg_insert(int* tab, int col) {
-    unsigned h = ((unsigned)col * 2654435761u) & (kSgHash - 1);
+    unsigned h = ((unsigned)col * 2654435761u) & (HASH - 1);
     while (true) {
         const int old = atomicCAS(tab + h, -1, col);
         if (old == -1) return true;
         if (old == col) return false;
-        h = (h + 1) & (kSgHash - 1);
+        h = (h + 1) & (HASH - 1);
     }
 }
 
 // mode 0: row_nnz[i] = number of distinct columns (or -1 on overflow)
 // mode 1: write the sorted columns at indices_c[indptr_c[i] ...]
+template <int kSgWarps, int kSgHash, int kSgCap>
 __global__ void __launch_bounds__(kSgWarps * 32)
 spgemm_symbolic_kernel(int m, const int* __restrict__ a_ptr, const int* __restrict__ a_idx,
                        const int* __restrict__ b_ptr, const int* __restrict__ b_idx, int* __restrict__ row_nnz,
@@ -45,7 +47,7 @@ spgemm_symbolic_kernel(int m, const int* __restrict__ a_ptr, const int* __restri
         const int k = a_idx[kk];
         const int bs = b_ptr[k], be_ = b_ptr[k + 1];
         if (be_ - bs > kSgCap) { overflow = true; break; }
-        for (int jj = bs + lane; jj < be_; jj += 32) cnt += sg_insert(t, b_idx[jj]) ? 1 : 0;
+        for (int jj = bs + lane; jj < be_; jj += 32) cnt += sg_insert<kSgHash>(t, b_idx[jj]) ? 1 : 0;
         // stop before the table can fill up (probing would not terminate on a full table)
         int tot = cnt;
 #pragma unroll
@@ -89,6 +91,7 @@ spgemm_symbolic_kernel(int m, const int* __restrict__ a_ptr, const int* __restri
     for (int s = lane; s < tot; s += 32) c_idx[cs + s] = L[s];
 }
 
+template <int kSgWarps, int kSgCap>
 __global__ void __launch_bounds__(kSgWarps * 32)
 spgemm_numeric_kernel(int m, const int* __restrict__ a_ptr, const int* __restrict__ a_idx,
                       const double* __restrict__ a_val, const int* __restrict__ b_ptr, const int* __restrict__ b_idx,
@@ -100,6 +103,7 @@ spgemm_numeric_kernel(int m, const int* __restrict__ a_ptr, const int* __restric
     const int row = blockIdx.x * kSgWarps + warp;
     if (row >= m) return;
     const int cs = c_ptr[row], n_c = c_ptr[row + 1] - cs;
+    if (n_c > kSgCap) return;                 // the host picks the class from the longest row; never taken
     int* C = cols[warp];
     double* A = acc[warp];
     for (int s = lane; s < n_c; s += 32) { C[s] = c_idx[cs + s]; A[s] = 0.0; }
@@ -128,8 +132,14 @@ extern "C" int hx_spgemm_symbolic(int m, const int32_t* a_ptr, const int32_t* a_
                                   const int32_t* b_idx, int32_t* row_nnz, const int32_t* c_ptr, int32_t* c_idx,
                                   int write_cols, hx_stream_t stream) {
     if (m <= 0) return HX_OK;
-    spgemm_symbolic_kernel<<<ceil_div(m, kSgWarps), kSgWarps * 32, 0, (cudaStream_t)stream>>>(
-        m, a_ptr, a_idx, b_ptr, b_idx, row_nnz, c_ptr, c_idx, write_cols);
+    // write_cols: 0 / 1 = count / fill with the large class (rows up to 2048 distinct columns);
+    //             2 / 3 = count / fill with the small class (up to 512; -1 in row_nnz on overflow)
+    if (write_cols >= 2)
+        spgemm_symbolic_kernel<8, 1024, 512><<<ceil_div(m, 8), 8 * 32, 0, (cudaStream_t)stream>>>(
+            m, a_ptr, a_idx, b_ptr, b_idx, row_nnz, c_ptr, c_idx, write_cols - 2);
+    else
+        spgemm_symbolic_kernel<2, 4096, 2048><<<ceil_div(m, 2), 2 * 32, 0, (cudaStream_t)stream>>>(
+            m, a_ptr, a_idx, b_ptr, b_idx, row_nnz, c_ptr, c_idx, write_cols);
     return check_launch("spgemm_symbolic_kernel");
 }
 
@@ -137,7 +147,17 @@ extern "C" int hx_spgemm_numeric(int m, const int32_t* a_ptr, const int32_t* a_i
                                  const int32_t* b_ptr, const int32_t* b_idx, const double* b_val,
                                  const int32_t* c_ptr, const int32_t* c_idx, double* c_val, hx_stream_t stream) {
     if (m <= 0) return HX_OK;
-    spgemm_numeric_kernel<<<ceil_div(m, kSgWarps), kSgWarps * 32, 0, (cudaStream_t)stream>>>(
+    spgemm_numeric_kernel<2, 2048><<<ceil_div(m, 2), 2 * 32, 0, (cudaStream_t)stream>>>(
         m, a_ptr, a_idx, a_val, b_ptr, b_idx, b_val, c_ptr, c_idx, c_val);
     return check_launch("spgemm_numeric_kernel");
+}
+
+/* same for a pattern whose longest row has at most 512 entries (8 warps per CTA) */
+extern "C" int hx_spgemm_numeric_small(int m, const int32_t* a_ptr, const int32_t* a_idx, const double* a_val,
+                                       const int32_t* b_ptr, const int32_t* b_idx, const double* b_val,
+                                       const int32_t* c_ptr, const int32_t* c_idx, double* c_val, hx_stream_t stream) {
+    if (m <= 0) return HX_OK;
+    spgemm_numeric_kernel<8, 512><<<ceil_div(m, 8), 8 * 32, 0, (cudaStream_t)stream>>>(
+        m, a_ptr, a_idx, a_val, b_ptr, b_idx, b_val, c_ptr, c_idx, c_val);
+    return check_launch("spgemm_numeric_kernel<small>");
 }

@@ -625,6 +625,9 @@ class _DLevel:
     pass
 
 
+SELL_MIN_ROWS = 250000      # owned rows of a distributed level from which its block is stored as SELL-32
+
+
 class DistHierarchy:
     """Replicated set-up, row-distributed cycle.  Levels with at least `min_rows` rows per rank are
     distributed (smoothing, residual, restriction and prolongation on the owned rows, one halo exchange
@@ -656,7 +659,11 @@ class DistHierarchy:
         coords = torch.zeros(ng, 3, dtype=space.dof_coords.dtype, device=dev)
         coords[_all_gather_rows(l2g[:n_own], world)] = _all_gather_rows(space.dof_coords, world)
         B = glob(base["B"]) if base.get("B") is not None else None
-        self.mg = mg = AMG(be, glob(base["A"]), glob(base["C"]), B, coords, **amg_options)
+        # the replicated hierarchy only feeds the owned rows of the distributed levels and runs the small levels:
+        # no SELL copies of the global operators (the distributed blocks build their own)
+        opts = dict(amg_options)
+        opts.setdefault("sell_min_rows", 1 << 62)
+        self.mg = mg = AMG(be, glob(base["A"]), glob(base["C"]), B, coords, **opts)
         mg.use_graph = False
         self.single, self.wdtype, self.nu = mg.single, mg.wdtype, mg.nu
         nlev = len(mg.levels)
@@ -702,7 +709,7 @@ class DistHierarchy:
             D.b = be.zeros(n_o, dtype=wd)
             D.dinv = be.zeros(n_o)
             D.sellp = None
-            if mg.sell_min_rows is not None and n_o >= mg.sell_min_rows:
+            if getattr(be, "supports_sell", False) and n_o >= SELL_MIN_ROWS:
                 from .sell import SellPattern
                 D.sellp = SellPattern(be, D.M_pat.indptr, D.M_pat.indices, n_o, n_l)
                 D.sell_vals = be.empty(max(D.sellp.total, 1), dtype=wd)

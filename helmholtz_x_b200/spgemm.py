@@ -7,16 +7,27 @@ from .backend import CsrMatrix
 f64 = torch.float64
 
 
+_longest = {}
+
+
 class Overflow(Exception):
     """A product row has more distinct columns than the kernel's shared-memory budget."""
 
 
+SMALL_CAP = 512          # rows of at most this many distinct columns use the 8-warps-per-CTA kernels
+
+
 def symbolic(be, A: CsrMatrix, B: CsrMatrix):
-    """Pattern (indptr, indices) of A*B."""
+    """Pattern (indptr, indices) of A*B.  The small size class first (fine levels), the large one on overflow."""
     m = A.n_rows
     row_nnz = be.zeros(max(m, 1), dtype=torch.int32)
+    mode = 2
     _lib.call("hx_spgemm_symbolic", m, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(), B.indices.data_ptr(),
-              row_nnz.data_ptr(), None, None, 0, be.stream)
+              row_nnz.data_ptr(), None, None, mode, be.stream)
+    if m and int(row_nnz.min()) < 0:
+        mode = 0
+        _lib.call("hx_spgemm_symbolic", m, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(), B.indices.data_ptr(),
+                  row_nnz.data_ptr(), None, None, mode, be.stream)
     if m and int(row_nnz.min()) < 0:
         raise Overflow()
     indptr = be.zeros(m + 1, dtype=torch.int64)
@@ -27,14 +38,19 @@ def symbolic(be, A: CsrMatrix, B: CsrMatrix):
     indptr = indptr.to(torch.int32).contiguous()
     indices = be.empty(max(nnz, 1), dtype=torch.int32)
     _lib.call("hx_spgemm_symbolic", m, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(), B.indices.data_ptr(),
-              row_nnz.data_ptr(), indptr.data_ptr(), indices.data_ptr(), 1, be.stream)
+              row_nnz.data_ptr(), indptr.data_ptr(), indices.data_ptr(), mode + 1, be.stream)
     return indptr, indices[:nnz]
 
 
 def numeric(be, A: CsrMatrix, B: CsrMatrix, indptr, indices, out=None):
     """Values of A*B on the given pattern (float64)."""
     out = out if out is not None else be.empty(max(int(indices.numel()), 1), dtype=f64)
-    _lib.call("hx_spgemm_numeric", A.n_rows, A.indptr.data_ptr(), A.indices.data_ptr(), A.values.data_ptr(),
+    key = (indptr.data_ptr(), int(indptr.numel()))
+    if _longest.get("key") != key:                       # longest row of the pattern (one sync per pattern)
+        _longest["key"] = key
+        _longest["len"] = int((indptr[1:] - indptr[:-1]).max()) if indptr.numel() > 1 else 0
+    name = "hx_spgemm_numeric_small" if _longest["len"] <= SMALL_CAP else "hx_spgemm_numeric"
+    _lib.call(name, A.n_rows, A.indptr.data_ptr(), A.indices.data_ptr(), A.values.data_ptr(),
               B.indptr.data_ptr(), B.indices.data_ptr(), B.values.data_ptr(), indptr.data_ptr(), indices.data_ptr(),
               out.data_ptr(), be.stream)
     return out[:indices.numel()]

@@ -214,6 +214,12 @@ int hx_spgemm_symbolic(int m, const int32_t* a_ptr, const int32_t* a_idx, const 
 int hx_spgemm_numeric(int m, const int32_t* a_ptr, const int32_t* a_idx, const double* a_val,
                       const int32_t* b_ptr, const int32_t* b_idx, const double* b_val,
                       const int32_t* c_ptr, const int32_t* c_idx, double* c_val, hx_stream_t stream);
+/* size classes: hx_spgemm_symbolic with write_cols 2 / 3 (count / fill) and hx_spgemm_numeric_small serve rows of at
+ * most 512 distinct columns with 8 warps per CTA (the fine levels); overflow is reported as -1 in row_nnz and the
+ * caller repeats with the large class */
+int hx_spgemm_numeric_small(int m, const int32_t* a_ptr, const int32_t* a_idx, const double* a_val,
+                            const int32_t* b_ptr, const int32_t* b_idx, const double* b_val,
+                            const int32_t* c_ptr, const int32_t* c_idx, double* c_val, hx_stream_t stream);
 
 /* ------------------------------------------------------------------ K4
  * DOLFINx SparsityPattern + MatCreateAIJ (acoustic_matrices.py:102): CSR pattern

@@ -420,6 +420,15 @@ def test_spgemm_kernels_match_scipy_and_are_deterministic():
     D = sp.identity(n, format="csr")
     with pytest.raises(spgemm.Overflow):
         spgemm.multiply(b, dev(wide), dev(D))
+    # a product with rows of 513..1500 distinct columns: the small size class overflows, the large one takes over
+    m = 40
+    rows = np.repeat(np.arange(m), 1500)
+    cols = np.concatenate([rng.choice(n, 1500, replace=False) for _ in range(m)])
+    W = sp.csr_matrix((rng.standard_normal(m * 1500), (rows, cols)), shape=(m, n))
+    Cw = spgemm.multiply(b, dev(W), dev(D))
+    ref = W.tocsr(); ref.sort_indices()
+    assert np.array_equal(Cw.indices.cpu().numpy(), ref.indices)
+    assert abs(sp.csr_matrix((Cw.values.cpu().numpy(), Cw.indices.cpu().numpy(), Cw.indptr.cpu().numpy()), shape=ref.shape) - ref).max() < 1e-14
 
 
 def test_ilu0_level_scheduled_matches_host_ilu0():
