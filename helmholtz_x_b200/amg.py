@@ -492,6 +492,8 @@ class AMG:
         # column-major storage of the coarse matrix == row-major storage of its transpose
         dense[L.M.indices.long(), rows] = L.M.values
         info = be.dense_inverse(dense)
+        if int(info[0]) != 0:          # one read per shift: an exactly singular coarsest operator would fill the cycle with NaNs
+            raise RuntimeError(f"multigrid: the coarsest operator is singular (zero pivot in column {int(info[0]) - 1})")
         self.coarse_inv = dense
         self._coarse_info = info
         self._tail = self._tail_descriptor()

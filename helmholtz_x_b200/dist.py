@@ -202,20 +202,11 @@ class Partition:
             out = np.zeros(self.n_global, complex)
             out[self.l2g[:self.n_own]] = x_own.cpu().numpy()
             return out
-        mx = int(self.own_counts.max())
-        pad = torch.zeros(mx, 2, dtype=torch.float64, device=x_own.device)
-        pad[:self.n_own] = torch.view_as_real(x_own.contiguous())
-        bufs = [torch.zeros_like(pad) for _ in range(self.world)]
-        all_gather_tensors(bufs, pad)
-        if getattr(self, "_all_ids", None) is None:           # static per partition
-            ids = [None] * self.world
-            dist.all_gather_object(ids, self.l2g[:self.n_own])
-            self._all_ids = ids
-        ids = self._all_ids
+        if getattr(self, "_all_ids", None) is None:           # static per partition; tensor collective, no pickling
+            self._all_ids = _all_gather_rows(self._d["l2g"][:self.n_own].contiguous(), self.world).cpu().numpy()
+        vals = _all_gather_rows(x_own[:self.n_own].contiguous(), self.world).cpu().numpy()
         out = np.zeros(self.n_global, complex)
-        for q in range(self.world):
-            v = bufs[q][:int(self.own_counts[q])].cpu().numpy()
-            out[ids[q]] = v[:, 0] + 1j * v[:, 1]
+        out[self._all_ids] = vals
         return out
 
 
@@ -499,6 +490,8 @@ class CoarseCorrection:
                 M += complex(v) * self.dense[k]
         self.inv = M.t().contiguous()          # column-major view of M for the in-place inverse kernel
         self.info = self.be.dense_inverse(self.inv)
+        if int(self.info[0]) != 0:
+            raise RuntimeError("multi-GPU coarse correction: the coarse operator is singular")
 
     def apply(self, v, x):
         """x = P0 A0^-1 P0^T v  (v, x: owned entries)."""
@@ -743,7 +736,17 @@ class DistHierarchy:
             else:
                 D.P = _csr_rows(L.P, D.own)                                       # own_l x n_{l+1} (replicated below)
                 D.R = _csr_transpose(D.P)                                         # partial sums, all-reduced
+            D.P, D.R = self._transfer_op(D.P), self._transfer_op(D.R)
         assert torch.equal(self.dl[0].own, l2g[:n_own]), "level-0 ownership differs from the partition"
+
+    def _transfer_op(self, M):
+        """SELL-32 copy of a float32 transfer block with many rows (as amg.AMG._transfer_op on one GPU)."""
+        if (not getattr(self.be, "supports_sell", False) or M.n_rows < SELL_MIN_ROWS or M.values is None
+                or M.values.dtype != torch.float32 or os.environ.get("HX_AMG_SELL_TRANSFER", "1") == "0"):
+            return M
+        from .sell import SellMatrix, SellPattern
+        p = SellPattern(self.be, M.indptr, M.indices, M.n_rows, M.n_cols)
+        return SellMatrix(p, p.values_from_csr(M.values))
 
     def set_fine(self, values_own=None):
         """Refresh the owned rows of every distributed level from the replicated level operators
