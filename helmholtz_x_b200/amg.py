@@ -502,10 +502,12 @@ class AMG:
     def _tail_descriptor(self):
         """Descriptor of the fused cycle tail (last smoothed level + dense coarsest solve, hx_amg_tail), or None
         when it does not apply: one level, complex128 cycle, that level stored as SELL, or not asked for.
-        OFF by default (HX_AMG_TAIL=1 switches it on): measured on B200 (profiles/r2_tail_*.json) one visit of the
-        tail drops from 82 to 42 us at 1 M DoF (1950 rows) but rises from 81 to 105 us at 5 M DoF (9760 rows x 180
-        nonzeros: one CTA per SM hides too little latency), and the graph-replayed cycle is slower in both cases
-        (466 -> 543 us, 1800 -> 2125 us); whole step 2.98 -> 3.23 s and 12.8 -> 13.8 s.  Kept as a tested option."""
+        OFF by default (HX_AMG_TAIL=1 switches it on).  Measured on B200 (profiles/r2_tail2_*.json, 4 CTAs per SM):
+        launched kernel by kernel one visit of the tail drops from 78 to 35 us at 1 M DoF and from 88 to 78 us at 8 M
+        DoF -- but the production cycle is replayed from a CUDA graph, where the ten small kernels of the unfused
+        tail already run back to back: the replayed cycle takes 498 us fused against 494 us unfused at 1 M DoF and the
+        whole step 2.95 s against 2.92 s (8 M: 20.3 s against 20.1 s).  The graph had already removed the latency the
+        fusion was after; kept as a tested option.  (A first version with one CTA per SM was slower.)"""
         if (len(self.levels) < 2 or not self.single or not getattr(self.be, "supports_tail", False)
                 or os.environ.get("HX_AMG_TAIL", "0") != "1"):
             return None

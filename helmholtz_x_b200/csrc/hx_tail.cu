@@ -9,8 +9,9 @@
 namespace hx {
 
 constexpr int kTailThreads = 256;
+constexpr int kTailCtasPerSm = 4;      // co-resident by construction: 4 x 256 threads, <= 64 registers, no shared arrays
 
-// sense-reversing grid barrier; the grid is at most one CTA per SM (all co-resident)
+// sense-reversing grid barrier; the grid is at most kTailCtasPerSm CTAs per SM (all co-resident)
 __device__ __forceinline__ void tail_barrier(unsigned int* bar, unsigned int nblocks) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -48,7 +49,7 @@ __device__ __forceinline__ float2 tail_row(const int* __restrict__ ptr, const in
     return warp_sum(acc);
 }
 
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailThreads, kTailCtasPerSm)
 tail_kernel(hx_tail_desc a, const float2* __restrict__ b) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kTailThreads + threadIdx.x) >> 5;
@@ -124,7 +125,7 @@ using namespace hx;
 extern "C" int hx_amg_tail(const hx_tail_desc* d, const float* b_c64, hx_stream_t stream) {
     if (!d || d->n <= 0 || d->nc <= 0 || d->nu < 1 || d->nu > 4) return fail(HX_ERR_ARG, "hx_amg_tail: bad descriptor%s%s");
     int grid = ceil_div(d->n * 32, kTailThreads);          // one warp per row is all the parallelism there is
-    if (grid > kNumSMs) grid = kNumSMs;                    // <= one CTA per SM: the barrier needs co-residency
+    if (grid > kNumSMs * kTailCtasPerSm) grid = kNumSMs * kTailCtasPerSm;   // the barrier needs co-residency
     if (grid < 1) grid = 1;
     tail_kernel<<<grid, kTailThreads, 0, (cudaStream_t)stream>>>(*d, (const float2*)b_c64);
     return check_launch("tail_kernel");
