@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-HOT = ("sell_kernel", "spmv_csr_kernel", "jacobi_kernel", "multi_dot_kernel", "multi_axpy_kernel", "scale_copy_kernel",
+HOT = ("tail_kernel", "sell_kernel", "spmv_csr_kernel", "jacobi_kernel", "multi_dot_kernel", "multi_axpy_kernel", "scale_copy_kernel",
        "basis_rotate", "halo_exchange_kernel", "allreduce_kernel", "color_round_kernel", "assemble_AC_kernel",
        "dense_gemv_kernel", "spgemm_numeric_kernel")
 
