@@ -247,6 +247,9 @@ def _p2_worker(rank, world, port, q):
         assert np.all(np.diff(dpart.l2g[:dpart.n_own]) > 0)                       # ascending global ids
         assert dpart.n_ghost > 0 and (dpart.owner[dpart.l2g[dpart.n_own:]] != rank).all()
         gl_old = dpart.l2g[dpart.dof_inv_perm]                                    # global dof of every dof of the local space
+        assert np.array_equal(dpart.g2l_old[gl_old], np.arange(len(gl_old)))       # Dirichlet dofs go through this map
+        assert np.array_equal(dpart.g2l[dpart.l2g], np.arange(len(gl_old))) and (dpart.g2l_old >= 0).sum() == len(gl_old)
+        assert np.array_equal(gl_old[:part.n_loc], part.l2g)                       # vertex dofs first, in sub-mesh order
 
         class FakeV:
             degree = 2
